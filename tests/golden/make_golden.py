@@ -1,0 +1,189 @@
+"""
+Generate the golden vectors in this directory from the LIVE, UNMODIFIED reference.
+
+Run in the build container only (the reference is mounted at /root/reference
+there and exists nowhere else):
+
+    PYTHONPATH=/root/reference:/root/repo python tests/golden/make_golden.py
+
+Inputs and weights are pure functions of their names
+(vq_voice_swap_b200.synth), so only the reference's OUTPUTS are stored.  The
+tests replay these files against oracle/ (CPU) and against the CUDA path (GPU).
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import vq_voice_swap  # noqa: E402  (must resolve to the reference)
+
+assert vq_voice_swap.__file__.startswith("/root/reference"), vq_voice_swap.__file__
+
+from vq_voice_swap.diffusion import Diffusion, make_schedule  # noqa: E402
+from vq_voice_swap.diffusion_model import DiffusionModel  # noqa: E402
+from vq_voice_swap.models.unet import ResBlock, UNetEncoder  # noqa: E402
+from vq_voice_swap.vq import VQ  # noqa: E402
+from vq_voice_swap.vq_vae import VQVAE  # noqa: E402
+
+from vq_voice_swap_b200 import synth  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name), **{k: np.asarray(v) for k, v in arrays.items()})
+    print("wrote", name, {k: np.asarray(v).shape for k, v in arrays.items()})
+
+
+# Shared with the tests: the case tables live in cases.py so both sides agree.
+from cases import DDPM_CASES, RESBLOCK_CASES  # noqa: E402
+
+
+def resblocks():
+    out = {}
+    for name, kw in RESBLOCK_CASES.items():
+        blk = ResBlock(**kw["ctor"]).eval()
+        synth.load_synth(blk, tag=f"rb/{name}")
+        x = synth.normal(f"rb/{name}/x", (kw["batch"], kw["ctor"]["channels"], kw["t"]))
+        emb = None
+        if kw["ctor"].get("emb_channels"):
+            emb = synth.normal(f"rb/{name}/emb", (kw["batch"], kw["ctor"]["emb_channels"]))
+        out[name] = blk(x, emb).numpy()
+    save("resblocks.npz", **out)
+
+
+def unet_small():
+    out = {}
+    m = DiffusionModel("unet", 16).eval()
+    synth.load_synth(m, tag="unet16")
+    x = synth.normal("unet16/x", (2, 1, 512))
+    ts = torch.tensor([0.9, 0.3])
+    out["uncond"] = m.predictor(x, ts).numpy()
+
+    m = DiffusionModel("unet", 16, num_labels=5, cond_channels=48).eval()
+    synth.load_synth(m, tag="unet16c")
+    cond = synth.normal("unet16c/cond", (2, 48, 2))
+    labels = torch.tensor([4, 1])
+    out["cond"] = m.predictor(x, ts, cond=cond, labels=labels).numpy()
+
+    enc = UNetEncoder(16, out_channels=48).eval()
+    synth.load_synth(enc, tag="enc16")
+    out["encoder"] = enc(x).numpy()
+    save("unet_bc16.npz", **out)
+
+
+def vq_cases():
+    vq = VQ(48, 96).eval()
+    synth.load_synth(vq, tag="vq")
+    x = synth.normal("vq/x", (3, 48, 40))
+    res = vq(x)
+    # exact duplicate dictionary rows -> first-index tie-break must be visible
+    vq2 = VQ(16, 32).eval()
+    sd = synth.synth_state_dict(synth.shapes_of(vq2), tag="vq2")
+    sd["dictionary"][20] = sd["dictionary"][7]
+    sd["dictionary"][31] = sd["dictionary"][7]
+    vq2.load_state_dict(sd)
+    x2 = sd["dictionary"][synth.integers("vq2/pick", (2, 50), 32)].permute(0, 2, 1).contiguous()
+    x2 = x2 + 0.01 * synth.normal("vq2/jitter", x2.shape)
+    save(
+        "vq.npz",
+        idxs=res["idxs"].numpy(),
+        embedded=res["embedded"].numpy(),
+        idxs_ties=vq2(x2)["idxs"].numpy(),
+        embed_from_idx=vq.embed(synth.integers("vq/codes", (2, 7), 96)).numpy(),
+    )
+
+
+class _Inject:
+    """Replace torch.randn / randn_like by deterministic synthetic draws."""
+
+    def __init__(self, tag):
+        self.tag, self.n = tag, 0
+
+    def __enter__(self):
+        self._randn, self._like = torch.randn, torch.randn_like
+        torch.randn = lambda *shape, **kw: synth.normal(f"{self.tag}/x_T", shape if not isinstance(shape[0], (tuple, list)) else shape[0])
+
+        def like(x, **kw):
+            t = synth.normal(f"{self.tag}/noise{self.n}", x.shape)
+            self.n += 1
+            return t.to(x)
+
+        torch.randn_like = like
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._randn, self._like
+
+
+def ddpm():
+    out = {}
+    for name, kw in DDPM_CASES.items():
+        diff = Diffusion(make_schedule(kw["schedule"]))
+        x_t = synth.normal(f"ddpm/{name}/x", (3, 1, 96), std=kw.get("x_std", 1.0))
+        eps = synth.normal(f"ddpm/{name}/eps", (3, 1, 96))
+        noise = synth.normal(f"ddpm/{name}/noise", (3, 1, 96))
+        ts = torch.tensor(kw["ts"], dtype=torch.float32)
+        cond_fn = (lambda x, t: torch.sin(x) * t[:, None, None]) if kw.get("cond_fn") else None
+        out[name] = diff.ddpm_previous(
+            x_t, ts, kw["step"], eps, noise=noise, sigma_large=kw.get("sigma_large", False),
+            constrain=kw.get("constrain", False), cond_fn=cond_fn,
+        ).numpy()
+
+    # whole sampler loop on a closed-form predictor; with and without sample-time schedule
+    toy = lambda x, ts: 0.7 * x * ts[:, None, None] + 0.1
+    for name, sched, constrain in [("loop_plain", None, False), ("loop_sq", lambda t: t ** 2, True)]:
+        diff = Diffusion(make_schedule("exp"))
+        x_T = synth.normal(f"ddpm/{name}/x_T", (2, 1, 64))
+        with _Inject(f"ddpm/{name}"):
+            out[name] = diff.ddpm_sample(x_T, toy, 6, constrain=constrain, schedule=sched).numpy()
+    save("ddpm.npz", **out)
+
+
+def vqvae_small():
+    m = VQVAE(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet").eval()
+    synth.load_synth(m, tag="vqvae16")
+    w = synth.normal("vqvae16/wave", (2, 1, 512)).clamp(-1, 1)
+    codes = m.encode(w)
+    enc_out = m.encoder(w)
+    labels = torch.tensor([2, 0])
+    with _Inject("vqvae16/decode"):
+        audio = m.decode(codes, labels, steps=3, constrain=True)
+    save("vqvae_bc16.npz", codes=codes.numpy(), encoder_out=enc_out.numpy(), audio=audio.numpy())
+
+
+def keys():
+    specs = {
+        "diffusion_unet32": DiffusionModel("unet", 32),
+        "diffusion_unet16_cond": DiffusionModel("unet", 16, num_labels=5, cond_channels=48),
+        "diffusion_unet16_dropout": DiffusionModel("unet", 16, dropout=0.1),
+        "vqvae_unet32": VQVAE(base_channels=32, pred_name="unet", num_labels=8),
+        "diffusion_unet16": DiffusionModel("unet", 16),
+        "vqvae16": VQVAE(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet"),
+    }
+    table = {
+        n: [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()] for n, m in specs.items()
+    }
+    table["save_kwargs"] = {n: m.save_kwargs() for n, m in specs.items()}
+    table["encoder16"] = [[k, list(v.shape), str(v.dtype)] for k, v in UNetEncoder(16, out_channels=48).state_dict().items()]
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump(table, f)
+    print("wrote state_dict_keys.json", {k: len(v) for k, v in table.items()})
+
+
+if __name__ == "__main__":
+    if sys.argv[1:] == ["keys"]:
+        keys()
+        sys.exit(0)
+    resblocks()
+    unet_small()
+    vq_cases()
+    ddpm()
+    vqvae_small()
+    keys()
