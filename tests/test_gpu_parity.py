@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden outputs and the oracle.
+
+Tolerances (relative L2 unless stated), from BASELINE.json north_star: 1e-3 relative fp32 for
+floating point, bit-exact for VQ indices.  The fp32 CUDA-core kernels are held to 2e-5, the
+tcgen05 bf16x3 kernels to 1e-4 per ResBlock.
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cases import DDPM_CASES, RESBLOCK_CASES
+from helpers import model_sd, rel_l2, resblock_case, shapes_from_table, key_table
+from oracle import hotpath as O
+from vq_voice_swap_b200 import lib as L
+from vq_voice_swap_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"simt": 2e-5, "umma": 1e-4}
+DEV = "cuda:0"
+
+
+@pytest.fixture(params=["simt", "umma"])
+def backend(request, monkeypatch):
+    monkeypatch.setenv("VQVS_BACKEND", request.param)
+    return request.param
+
+
+# ---------------------------------------------------------------------------
+# tcgen05 building block
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,shift,variant,tol", [
+    (64, 64, 0, 0, 2e-5), (64, 64, 3, 0, 2e-5), (256, 32, 64, 0, 2e-5), (16, 16, 1, 0, 2e-5),
+    (128, 192, 2, 0, 2e-5), (64, 64, 0, 2, 1e-2),
+])
+def test_umma_selftest(n, k, shift, variant, tol):
+    lib = L.load()
+    a = synth.normal(f"st/a{n}{k}{shift}", (128 + shift, k)).to(DEV)
+    b = synth.normal(f"st/b{n}{k}{shift}", (n, k)).to(DEV)
+    d = torch.full((128, n), float("nan"), device=DEV)
+    L.check(lib.vqvs_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, shift, variant, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = a[shift:shift + 128].double() @ b.double().T
+    assert rel_l2(d.cpu(), ref.cpu()) <= tol
+
+
+# ---------------------------------------------------------------------------
+# ResBlocks against the live-reference golden vectors
+# ---------------------------------------------------------------------------
+def _our_resblock(name, kw):
+    from vq_voice_swap_b200.unet import ResBlock
+
+    sd, x, emb = resblock_case(name, kw)
+    blk = ResBlock(**kw["ctor"])
+    blk.load_state_dict(sd)
+    blk = blk.to(DEV).eval()
+    return blk, x.to(DEV), None if emb is None else emb.to(DEV)
+
+
+@pytest.mark.parametrize("name", sorted(RESBLOCK_CASES))
+def test_resblock_golden(golden, backend, name):
+    blk, x, emb = _our_resblock(name, RESBLOCK_CASES[name])
+    y = blk(x, emb)
+    assert rel_l2(y.cpu(), golden("resblocks.npz")[name]) <= TOL[backend]
+
+
+def test_umma_is_actually_selected(monkeypatch):
+    """The tcgen05 kernel, not the SIMT fallback, must carry the standard shapes."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    blk, x, emb = _our_resblock("plain_film", RESBLOCK_CASES["plain_film"])
+    blk(x, emb)
+    plan = next(iter(blk._plans.items.values()))
+    kinds = [k for k, _ in plan.descs]
+    assert kinds.count(L.OP_CONV_UMMA) == 2 and L.OP_CONV_SIMT not in kinds
+
+
+# ---------------------------------------------------------------------------
+# whole networks (bc = 16) against golden
+# ---------------------------------------------------------------------------
+def _diffusion_model(table, tag, **kw):
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    m = DiffusionModel("unet", 16, **kw)
+    m.load_state_dict(model_sd(table, tag))
+    return m.to(DEV).eval()
+
+
+def test_unet_predictor_uncond(golden, backend):
+    m = _diffusion_model("diffusion_unet16", "unet16")
+    x = synth.normal("unet16/x", (2, 1, 512)).to(DEV)
+    y = m.predictor(x, torch.tensor([0.9, 0.3], device=DEV))
+    assert rel_l2(y.cpu(), golden("unet_bc16.npz")["uncond"]) <= 10 * TOL[backend]
+
+
+def test_unet_predictor_cond(golden, backend):
+    m = _diffusion_model("diffusion_unet16_cond", "unet16c", num_labels=5, cond_channels=48)
+    x = synth.normal("unet16/x", (2, 1, 512)).to(DEV)
+    cond = synth.normal("unet16c/cond", (2, 48, 2)).to(DEV)
+    y = m.predictor(x, torch.tensor([0.9, 0.3], device=DEV), cond=cond, labels=torch.tensor([4, 1], device=DEV))
+    assert rel_l2(y.cpu(), golden("unet_bc16.npz")["cond"]) <= 10 * TOL[backend]
+
+
+def test_unet_encoder(golden, backend):
+    from vq_voice_swap_b200.unet import UNetEncoder
+
+    enc = UNetEncoder(16, out_channels=48)
+    enc.load_state_dict(model_sd("encoder16", "enc16"))
+    enc = enc.to(DEV).eval()
+    y = enc(synth.normal("unet16/x", (2, 1, 512)).to(DEV))
+    assert rel_l2(y.cpu(), golden("unet_bc16.npz")["encoder"]) <= 10 * TOL[backend]
+
+
+# ---------------------------------------------------------------------------
+# VQ: bit-exact indices
+# ---------------------------------------------------------------------------
+def _vq(num_channels, num_codes, dictionary):
+    from vq_voice_swap_b200.vq import VQ
+
+    vq = VQ(num_channels, num_codes)
+    with torch.no_grad():
+        vq.dictionary.copy_(dictionary)
+    return vq.to(DEV).eval()
+
+
+def test_vq_golden(golden):
+    g = golden("vq.npz")
+    d = synth.normal("vq/dictionary", (96, 48))
+    vq = _vq(48, 96, d)
+    out = vq(synth.normal("vq/x", (3, 48, 40)).to(DEV))
+    assert out["idxs"].dtype == torch.int64
+    assert np.array_equal(out["idxs"].cpu().numpy(), g["idxs"])
+    assert np.array_equal(out["embedded"].cpu().numpy(), g["embedded"])
+    codes = synth.integers("vq/codes", (2, 7), 96).to(DEV)
+    assert np.array_equal(vq.embed(codes).cpu().numpy(), g["embed_from_idx"])
+
+
+def test_vq_ties_first_index(golden):
+    d = synth.normal("vq2/dictionary", (32, 16))
+    d[20] = d[7]
+    d[31] = d[7]
+    x = d[synth.integers("vq2/pick", (2, 50), 32)].permute(0, 2, 1).contiguous()
+    x = x + 0.01 * synth.normal("vq2/jitter", x.shape)
+    idx = _vq(16, 32, d)(x.to(DEV))["idxs"].cpu().numpy()
+    assert np.array_equal(idx, golden("vq.npz")["idxs_ties"])
+
+
+def test_vq_config3_shape_vs_oracle():
+    """8000 vectors x 512 codes x 512 channels (BASELINE config 3): exact wherever the oracle's top-2
+    gap exceeds 64 ulp of the distance magnitude; sub-margin disagreements are counted and bounded."""
+    d = synth.normal("vq3/dictionary", (512, 512))
+    x = synth.normal("vq3/x", (32, 512, 250))
+    ref = O.vq_encode(d, x)
+    gap, mag = O.vq_top2_gap(d, x)
+    ours = _vq(512, 512, d)(x.to(DEV))["idxs"].cpu()
+    margin = 64 * np.finfo(np.float32).eps * mag
+    decisive = gap > margin
+    assert torch.equal(ours[decisive], ref[decisive])
+    undecided = int((~decisive).sum())
+    mismatched = int((ours != ref).sum())
+    assert mismatched <= undecided
+    assert undecided <= 0.01 * ref.numel()
+
+
+def test_vq_train_mode_tracks_usage():
+    """reference sample_vqvae.py never calls .eval(); its VQ crashes there on numpy>=1.24."""
+    d = synth.normal("vq/dictionary", (96, 48))
+    vq = _vq(48, 96, d).train()
+    out = vq(synth.normal("vq/x", (3, 48, 40)).to(DEV))
+    used = torch.zeros(96, dtype=torch.bool)
+    used[out["idxs"].cpu().unique()] = True
+    uc = vq.usage_count.cpu()
+    assert (uc[used] == 100).all() and (uc[~used] == 99).all()
+
+
+# ---------------------------------------------------------------------------
+# DDPM step and sampler loop
+# ---------------------------------------------------------------------------
+def _diffusion(name):
+    from vq_voice_swap_b200.diffusion import Diffusion, make_schedule
+
+    return Diffusion(make_schedule(name))
+
+
+@pytest.mark.parametrize("name", sorted(DDPM_CASES))
+def test_ddpm_previous_golden(golden, name):
+    kw = DDPM_CASES[name]
+    x_t = synth.normal(f"ddpm/{name}/x", (3, 1, 96), std=kw.get("x_std", 1.0)).to(DEV)
+    eps = synth.normal(f"ddpm/{name}/eps", (3, 1, 96)).to(DEV)
+    noise = synth.normal(f"ddpm/{name}/noise", (3, 1, 96)).to(DEV)
+    cond_fn = (lambda x, t: torch.sin(x) * t[:, None, None]) if kw.get("cond_fn") else None
+    y = _diffusion(kw["schedule"]).ddpm_previous(
+        x_t, torch.tensor(kw["ts"], device=DEV), kw["step"], eps, noise=noise,
+        sigma_large=kw.get("sigma_large", False), constrain=kw.get("constrain", False), cond_fn=cond_fn)
+    # coefficients come from the GPU's exp/rsqrt (like the reference on GPU): a few ulp from the CPU golden
+    assert rel_l2(y.cpu(), golden("ddpm.npz")[name]) <= 5e-6
+
+
+class _Noise:
+    """Same injection as make_golden._Inject, on the device."""
+
+    def __init__(self, tag, monkeypatch):
+        self.n = 0
+
+        def like(x, **kw):
+            t = synth.normal(f"{tag}/noise{self.n}", x.shape)
+            self.n += 1
+            return t.to(x)
+
+        monkeypatch.setattr(torch, "randn_like", like)
+
+
+@pytest.mark.parametrize("name,sched,constrain", [("loop_plain", None, False), ("loop_sq", lambda t: t ** 2, True)])
+def test_ddpm_sample_generic_predictor(golden, monkeypatch, name, sched, constrain):
+    toy = lambda x, ts: 0.7 * x * ts[:, None, None] + 0.1
+    x_T = synth.normal(f"ddpm/{name}/x_T", (2, 1, 64)).to(DEV)
+    _Noise(f"ddpm/{name}", monkeypatch)
+    y = _diffusion("exp").ddpm_sample(x_T, toy, 6, constrain=constrain, schedule=sched)
+    assert rel_l2(y.cpu(), golden("ddpm.npz")[name]) <= 2e-5
+
+
+def test_vqvae_encode_decode_golden(golden, monkeypatch, backend):
+    from vq_voice_swap_b200.vq_vae import VQVAE
+
+    g = golden("vqvae_bc16.npz")
+    m = VQVAE(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet")
+    m.load_state_dict(model_sd("vqvae16", "vqvae16"))
+    m = m.to(DEV)  # deliberately NOT .eval(): reference sample_vqvae.py:18-22
+    w = synth.normal("vqvae16/wave", (2, 1, 512)).clamp(-1, 1).to(DEV)
+    assert rel_l2(m.encoder(w).cpu(), g["encoder_out"]) <= 10 * TOL[backend]
+    codes = m.encode(w)
+    assert np.array_equal(codes.cpu().numpy(), g["codes"])
+    monkeypatch.setattr(torch, "randn", lambda *s, **k: synth.normal("vqvae16/decode/x_T", s))
+    _Noise("vqvae16/decode", monkeypatch)
+    audio = m.decode(codes, torch.tensor([2, 0], device=DEV), steps=3, constrain=True)
+    assert rel_l2(audio.cpu(), g["audio"]) <= 1e-3
+
+
+def test_fused_sampler_matches_unfused(monkeypatch, backend):
+    """ddpm_sample with the update fused into the UNet's last kernel == predictor() + ddpm_previous()."""
+    m = _diffusion_model("diffusion_unet16", "unet16")
+    x_T = synth.normal("fuse/x_T", (2, 1, 512)).to(DEV)
+    for constrain in (False, True):
+        _Noise("fuse", monkeypatch)
+        fused = m.diffusion.ddpm_sample(x_T, m.predictor, 3, constrain=constrain)
+        _Noise("fuse", monkeypatch)
+        unfused = m.diffusion.ddpm_sample(x_T, lambda x, t: m.predictor(x, t), 3, constrain=constrain)
+        assert rel_l2(fused.cpu(), unfused.cpu()) <= 1e-6
+
+
+def test_cpu_tensors_fail_loudly():
+    m = _diffusion_model("diffusion_unet16", "unet16")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.predictor(torch.zeros(1, 1, 512), torch.zeros(1))

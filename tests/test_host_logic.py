@@ -1,0 +1,175 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, the ctypes
+mirrors match the C structs, and the host modules keep the reference's API surface."""
+
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import key_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vqvs.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    ge.build()
+    from vq_voice_swap_b200 import lib
+
+    return lib
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vqvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = built.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vqvs.h but not exported"
+    assert sorted(built.SIGNATURES) == declared
+    assert lib.vqvs_abi_version() == built.ABI_VERSION
+
+
+def test_ctypes_structs_match_header(built, tmp_path):
+    names = {"VqvsConv": built.Conv, "VqvsGnFinalize": built.GnFinalize, "VqvsConvIn": built.ConvIn,
+             "VqvsConvOut": built.ConvOut, "VqvsDdpmFinish": built.DdpmFinish, "VqvsTimeEmbed": built.TimeEmbed,
+             "VqvsFilm": built.Film, "VqvsMemset": built.Memset, "VqvsOp": built.Op}
+    lines = []
+    for cname, ct in names.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vqvs.h"\nint main(void){' + "".join(lines) + "return 0;}")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in names.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for field, _ in ct._fields_:
+            assert int(out[f"{cname}.{field}"]) == getattr(ct, field).offset, f"{cname}.{field}"
+
+
+def test_bad_arguments_return_errors_not_crashes(built):
+    lib = built.load()
+    d = built.Conv()  # all zero
+    assert lib.vqvs_conv1d_fused(C.byref(d), None) == -1
+    assert b"conv" in lib.vqvs_last_error()
+    assert lib.vqvs_run(None, 3, None) == -1
+    assert lib.vqvs_packed_weight_bytes(64, 24, 3, 0) == -1  # 24 channels: not a multiple of 16
+    assert lib.vqvs_packed_weight_bytes(64, 128, 3, 128) == (128 * 3 + 128) * 64 * 4
+
+
+STATE_TABLES = {
+    "diffusion_unet32": lambda: _dm("unet", 32),
+    "diffusion_unet16": lambda: _dm("unet", 16),
+    "diffusion_unet16_cond": lambda: _dm("unet", 16, num_labels=5, cond_channels=48),
+    "diffusion_unet16_dropout": lambda: _dm("unet", 16, dropout=0.1),
+    "vqvae_unet32": lambda: _vqvae(base_channels=32, pred_name="unet", num_labels=8),
+    "vqvae16": lambda: _vqvae(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet"),
+}
+
+
+def _dm(*a, **k):
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    return DiffusionModel(*a, **k)
+
+
+def _vqvae(**k):
+    from vq_voice_swap_b200.vq_vae import VQVAE
+
+    return VQVAE(**k)
+
+
+@pytest.mark.parametrize("name", sorted(STATE_TABLES))
+def test_state_dict_layout_equals_reference(name):
+    m = STATE_TABLES[name]()
+    mine = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert mine == key_table()[name]
+    assert m.save_kwargs() == key_table()["save_kwargs"][name]
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    m = _dm("unet", 16, num_labels=3)
+    path = str(tmp_path / "m.pt")
+    m.save(path)
+    blob = torch.load(path, map_location="cpu")
+    assert set(blob) == {"kwargs", "state_dict"}
+    m2 = type(m).load(path)
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_zero_init_conventions():
+    """Output convs start at zero, FiLM Linear at 0.1x (reference models/unet.py:277,286-294)."""
+    from vq_voice_swap_b200.unet import ResBlock
+
+    torch.manual_seed(0)
+    blk = ResBlock(32, emb_channels=64, out_channels=64)
+    assert float(blk.post_cond[1].weight.abs().max()) == 0.0
+    assert float(blk.post_cond[1].bias.abs().max()) == 0.0
+    torch.manual_seed(0)
+    torch.nn.Conv1d(32, 64, 1)
+    ref = torch.nn.Linear(64, 128)
+    assert torch.allclose(blk.cond_layers[1].weight, ref.weight * 0.1)
+
+
+def test_factories_and_errors():
+    from vq_voice_swap_b200.diffusion import CosSchedule, ExpSchedule, make_schedule
+    from vq_voice_swap_b200.make import make_encoder, make_predictor
+
+    assert isinstance(make_schedule("exp"), ExpSchedule) and isinstance(make_schedule("cos"), CosSchedule)
+    with pytest.raises(ValueError, match="unknown schedule"):
+        make_schedule("linear")
+    with pytest.raises(ValueError, match="unknown predictor"):
+        make_predictor("nope")
+    with pytest.raises(ValueError, match="unknown encoder"):
+        make_encoder("nope")
+    assert make_encoder("unet128", base_channels=16, cond_mult=2).downsample_rate == 128
+    p = make_predictor("unet", base_channels=16)
+    assert p.downsample_rate == 256
+    with pytest.raises(AssertionError, match="labels"):
+        p(torch.zeros(1, 1, 256), torch.zeros(1), labels=torch.zeros(1, dtype=torch.long))
+
+
+def test_schedules_match_closed_form():
+    from vq_voice_swap_b200.diffusion import make_schedule
+
+    t = torch.linspace(0, 1, 11)
+    assert torch.allclose(make_schedule("exp")(t), torch.exp(torch.log(torch.tensor(1e-5)) * t ** 2), atol=1e-7)
+    assert torch.allclose(make_schedule("cos")(t), torch.cos(t * torch.pi / 2) ** 2)
+    assert abs(float(make_schedule("exp")(torch.tensor(1.0))) - 1e-5) < 1e-9
+
+
+def test_no_cuda_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    p = _dm("unet", 16).predictor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p(torch.zeros(1, 1, 256), torch.zeros(1))
+
+
+def test_reference_namespace_shim():
+    """`import vq_voice_swap...` (what the reference's scripts do) resolves to this implementation."""
+    import vq_voice_swap
+    from vq_voice_swap.dataset import ChunkReader, ChunkWriter  # noqa: F401
+    from vq_voice_swap.diffusion_model import DiffusionModel
+    from vq_voice_swap.models import Classifier, EncoderPredictor  # noqa: F401
+    from vq_voice_swap.vq_vae import VQVAE
+
+    assert vq_voice_swap.__file__.startswith(ROOT)
+    assert DiffusionModel is type(_dm("unet", 16)) and VQVAE.__mro__[1] is DiffusionModel

@@ -1,0 +1,79 @@
+// libvqvs: error channel, device query and the program runner.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vqvs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int run_film(const VqvsFilm* f, void* stream);
+
+}  // namespace vqvs
+
+extern "C" int vqvs_abi_version(void) { return VQVS_ABI_VERSION; }
+
+extern "C" const char* vqvs_last_error(void) { return vqvs::g_err; }
+
+extern "C" int vqvs_device_info(int* cc, int* sm_count) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp p;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    vqvs::set_error("vqvs_device_info: %s", cudaGetErrorString(e));
+    return VQVS_ECUDA;
+  }
+  if (cc) *cc = p.major * 10 + p.minor;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_run(const VqvsOp* ops, int n_ops, void* stream) {
+  if (!ops || n_ops < 0) {
+    vqvs::set_error("vqvs_run: bad program");
+    return VQVS_EINVAL;
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    int rc = VQVS_OK;
+    const void* p = ops[i].desc;
+    switch (ops[i].kind) {
+      case VQVS_OP_CONV_SIMT: rc = vqvs_conv1d_fused((const VqvsConv*)p, stream); break;
+      case VQVS_OP_CONV_UMMA: rc = vqvs_conv1d_umma((const VqvsConv*)p, stream); break;
+      case VQVS_OP_GN_FINALIZE: rc = vqvs_gn_finalize((const VqvsGnFinalize*)p, stream); break;
+      case VQVS_OP_CONV_IN: rc = vqvs_conv_in((const VqvsConvIn*)p, stream); break;
+      case VQVS_OP_CONV_OUT: rc = vqvs_conv_out((const VqvsConvOut*)p, stream); break;
+      case VQVS_OP_TIME_EMBED: rc = vqvs_time_embed((const VqvsTimeEmbed*)p, stream); break;
+      case VQVS_OP_FILM: rc = vqvs::run_film((const VqvsFilm*)p, stream); break;
+      case VQVS_OP_DDPM_FINISH: rc = vqvs_ddpm_finish((const VqvsDdpmFinish*)p, stream); break;
+      case VQVS_OP_MEMSET: {
+        const VqvsMemset* m = (const VqvsMemset*)p;
+        cudaError_t e = cudaMemsetAsync(m->ptr, 0, (size_t)m->bytes, (cudaStream_t)stream);
+        if (e != cudaSuccess) {
+          vqvs::set_error("memset: %s", cudaGetErrorString(e));
+          rc = VQVS_ECUDA;
+        }
+        break;
+      }
+      default:
+        vqvs::set_error("unknown op kind %d", ops[i].kind);
+        rc = VQVS_EINVAL;
+    }
+    if (rc != VQVS_OK) {
+      char msg[400];
+      strncpy(msg, vqvs::g_err, sizeof(msg) - 1);
+      msg[sizeof(msg) - 1] = 0;
+      vqvs::set_error("vqvs_run: op %d (kind %d) failed: %s", i, ops[i].kind, msg);
+      return rc;
+    }
+  }
+  return VQVS_OK;
+}

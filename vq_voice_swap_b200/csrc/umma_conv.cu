@@ -1,0 +1,730 @@
+// tcgen05 / TMEM implicit-GEMM 1-D convolution for sm_100a.
+//
+//   D[t, co] = sum_{tap, ci} A_tap[t, ci] * W_tap[co, ci]      (M = 128 positions, N = co tile, K = ci)
+//
+// * A (activations) is produced IN-KERNEL: 256 producer threads read the raw fp32 input with
+//   coalesced loads, apply the fused prologue (GroupNorm/FiLM affine -> exact GELU -> pool /
+//   upsample / concat select), split every value into bf16 hi + bf16 lo and store it K-major,
+//   un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so the three
+//   conv taps are the SAME tile read through descriptors whose start address is shifted by
+//   tap*dilation rows -- the halo is staged once.
+// * W (weights) is pre-split into bf16 hi/lo and pre-arranged on the device into the exact smem
+//   image (vqvs_pack_conv_weights); one elected thread streams it with cp.async.bulk (TMA) onto an
+//   mbarrier.
+// * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), three MMAs per
+//   K block: hi*hi + lo*hi + hi*lo  ("bf16x3": ~2^-16 relative operand error, measured 1.5e-5 on a
+//   whole UNet forward vs 9.7e-4 for single TF32 -- tools/precision_study.py).
+// * The producer warps then read the accumulator back with tcgen05.ld, add bias / identity skip,
+//   store coalesced along time, and reduce per-channel (sum, sumsq) for the next GroupNorm with a
+//   transposing shuffle butterfly + fp64 atomics.
+// The optional 1x1 skip conv (reference models/unet.py:265-271) is extra K blocks over the raw input.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vqvs {
+namespace umma {
+
+constexpr int TILE_M = 128;
+constexpr int KBLK = 16;  // channels per MMA K block (kind::f16: K = 16)
+constexpr int PRODUCER_WARPS = 8;
+constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
+constexpr int TMA_WARP = PRODUCER_WARPS;
+constexpr int MMA_WARP = PRODUCER_WARPS + 1;
+constexpr int THREADS = (PRODUCER_WARPS + 2) * 32;
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_HEADER = 128;  // mbarriers + TMEM base holder
+
+// Host-computed geometry shared by the packer and the kernel.
+struct Geo {
+  int n_tiles, n_tile;      // output-channel tiling (n_tile <= 256, multiple of 16)
+  int nkb_main, nkb_skip;   // K blocks of the main taps / of the 1x1 skip
+  int kbs;                  // K blocks per pipeline stage
+  int pad, rows;            // halo and A rows (= 128 + 2*pad)
+  int stages, main_stages, skip_stages;
+  int tmem_cols;
+  int a_kb_bytes;           // A bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
+  int b_unit_main;          // W bytes per main K block: ksize taps x hi/lo x 2 chunks x n_tile rows x 16 B
+  int b_unit_skip;          // W bytes per skip K block
+  int stage_bytes;          // kbs * (a_kb_bytes + b_unit_main)
+  int a_stage_bytes;
+  int param_bytes;          // scale/shift staging
+  long long per_tile_bytes; // packed image bytes per N tile
+  int smem_bytes;
+};
+
+static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, Geo* g) {
+  if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
+  g->n_tiles = (c_out + 255) / 256;
+  if (c_out % g->n_tiles) return false;
+  g->n_tile = c_out / g->n_tiles;
+  if (g->n_tile % 16 || g->n_tile < 16) return false;
+  g->nkb_main = c_in / KBLK;
+  g->nkb_skip = c_skip / KBLK;
+  g->pad = (ksize / 2) * dilation;
+  g->rows = TILE_M + 2 * g->pad;
+  g->a_kb_bytes = g->rows * 64;
+  g->b_unit_main = ksize * g->n_tile * 64;
+  g->b_unit_skip = g->n_tile * 64;
+  int per_kb = g->a_kb_bytes + g->b_unit_main;
+  int kbs = (36 * 1024) / per_kb;
+  g->kbs = kbs < 1 ? 1 : (kbs > 4 ? 4 : kbs);
+  g->stage_bytes = g->kbs * per_kb;
+  g->a_stage_bytes = g->kbs * g->a_kb_bytes;
+  g->param_bytes = ((2 * c_in * 4) + 127) / 128 * 128;
+  const int fixed = SMEM_HEADER + g->param_bytes;
+  int stages = (110 * 1024 - fixed) / g->stage_bytes;  // two CTAs per SM when it fits
+  if (stages < 2) stages = (225 * 1024 - fixed) / g->stage_bytes;
+  if (stages < 2) return false;
+  g->stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+  g->main_stages = (g->nkb_main + g->kbs - 1) / g->kbs;
+  g->skip_stages = (g->nkb_skip + g->kbs - 1) / g->kbs;
+  int cols = 32;
+  while (cols < g->n_tile) cols *= 2;
+  g->tmem_cols = cols;
+  g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
+  g->smem_bytes = fixed + g->stages * g->stage_bytes;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t holder, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor: 16-B rows at a 16-B pitch inside an 8-row
+// core matrix, SBO between 8-row groups, LBO between the two 8-channel chunks of one K block.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------
+// prologue math
+// ---------------------------------------------------------------------------
+// GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
+// max |error| 4.2e-7 over [-12, 12] in fp32, tighter than ATen's own fp32 GELU (1.2e-6).
+__device__ __forceinline__ float gelu_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float half_erfc = 0.5f * p * t * e;  // 0.5*erfc(|x|/sqrt2)
+  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return x * phi;
+}
+
+// split 8 floats into bf16 hi / lo vectors (16 B each)
+__device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float r0 = v[2 * i] - __low2float(hb);
+    const float r1 = v[2 * i + 1] - __high2float(hb);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct Src {
+  const float* a;
+  const float* b;
+  int c_a, c_b, t_in, t_conv, resize;
+};
+
+// Stage one 16-B A element: 8 consecutive channels [c8, c8+8) at conv-input position tc -> row `row`.
+__device__ __forceinline__ void produce_item(const Src& s, int n, int c8, int tc, bool act, const float* sc,
+                                             const float* sh, uint8_t* a_hi, uint8_t* a_lo, int row) {
+  float v[8];
+  if (tc < 0 || tc >= s.t_conv) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  } else {
+    const float* base = c8 < s.c_a ? s.a + ((size_t)n * s.c_a + c8) * s.t_in
+                                   : s.b + ((size_t)n * s.c_b + (c8 - s.c_a)) * s.t_in;
+    if (s.resize == VQVS_RESIZE_DOWN2) {
+      float2 x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __ldg(reinterpret_cast<const float2*>(base + (size_t)e * s.t_in + 2 * tc));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (act) {
+          const float a0 = gelu_as(fmaf(x[e].x, sc[e], sh[e]));
+          const float a1 = gelu_as(fmaf(x[e].y, sc[e], sh[e]));
+          v[e] = 0.5f * (a0 + a1);
+        } else {
+          v[e] = 0.5f * (x[e].x + x[e].y);
+        }
+      }
+    } else {
+      const int ts = s.resize == VQVS_RESIZE_UP2 ? (tc >> 1) : tc;
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __ldg(base + (size_t)e * s.t_in + ts);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = act ? gelu_as(fmaf(x[e], sc[e], sh[e])) : x[e];
+    }
+  }
+  uint4 hi, lo;
+  split8(v, &hi, &lo);
+  *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
+  *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+}
+
+// Transposing butterfly: every lane holds v[0..31] (one row, 32 columns); afterwards lane l holds
+// in v[0] the sum over the 32 lanes (rows) of column l.  31 shuffles instead of 160.
+__device__ __forceinline__ float column_sums32(float* v, int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = upper ? v[i] : v[i + step];
+      const float keep = upper ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // bars[0..3] full_a, [4..7] full_b, [8..11] empty, [12] acc_full
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 13 * 8);
+  float* s_scale = reinterpret_cast<float*>(smem + SMEM_HEADER);
+  const int c_in = d.c_a + d.c_b;
+  float* s_shift = s_scale + c_in;
+  uint8_t* stage0 = smem + SMEM_HEADER + g.param_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.z, nt = blockIdx.y, t0 = blockIdx.x * TILE_M;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_a = [&](int s) { return bar0 + 8u * s; };
+  auto full_b = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t acc_full = bar0 + 8u * 12;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(full_a(s), PRODUCER_THREADS);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_holder), g.tmem_cols);
+  if (d.act) {
+    for (int i = threadIdx.x; i < c_in; i += THREADS) {
+      s_scale[i] = d.scale[(size_t)n * c_in + i];
+      s_shift[i] = d.shift[(size_t)n * c_in + i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int total_stages = g.main_stages + g.skip_stages;
+  const int ntaps = d.ksize;
+
+  if (warp < PRODUCER_WARPS) {
+    // =========================== producers ===========================
+    const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
+    const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
+    for (int st = 0; st < total_stages; ++st) {
+      const int s = st % g.stages;
+      const uint32_t ph = (st / g.stages) & 1;
+      mbar_wait(empty(s), ph ^ 1);
+      uint8_t* a_stage = stage0 + (size_t)s * g.stage_bytes;
+      const bool is_skip = st >= g.main_stages;
+      const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
+      const int kb_end = is_skip ? g.nkb_skip : g.nkb_main;
+      const int nk = min(g.kbs, kb_end - kb0);
+      const Src& src = is_skip ? skip_src : main_src;
+      const bool act = !is_skip && d.act;
+      const int pad = is_skip ? 0 : g.pad;
+      // main rows: one item = (8-channel chunk q, position m)
+      for (int i = threadIdx.x; i < nk * 2 * TILE_M; i += PRODUCER_THREADS) {
+        const int q = i >> 7, m = i & (TILE_M - 1);
+        const int c8 = kb0 * KBLK + q * 8;
+        uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+        uint8_t* a_lo = a_hi + g.rows * 32;
+        produce_item(src, n, c8, t0 + m, act, s_scale + c8, s_shift + c8, a_hi, a_lo, pad + m);
+      }
+      // halo rows [0,pad) and [128+pad, 128+2*pad)
+      const int n_halo = nk * 2 * 2 * pad;
+      for (int i = threadIdx.x; i < n_halo; i += PRODUCER_THREADS) {
+        const int q = i / (2 * pad), e = i - q * (2 * pad);
+        const int row = e < pad ? e : TILE_M + e;
+        const int c8 = kb0 * KBLK + q * 8;
+        uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+        uint8_t* a_lo = a_hi + g.rows * 32;
+        produce_item(src, n, c8, t0 - pad + row, act, s_scale + c8, s_shift + c8, a_hi, a_lo, row);
+      }
+      fence_proxy_async();
+      mbar_arrive(full_a(s));
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;           // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = warp >> 2;             // the two warps of a quarter split the columns
+    const int row = quarter * 32 + lane;
+    const int t = t0 + row;
+    const bool t_ok = t < d.t_out;
+    const int n_chunks32 = g.n_tile / 32;
+    for (int ch = half; ch < n_chunks32; ch += 2) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, v);
+      const int co0 = nt * g.n_tile + ch * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int co = co0 + j;
+        float b = d.bias ? __ldg(d.bias + co) : 0.f;
+        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += __ldg(d.b_skip + co);
+        float o = v[j] + b;
+        if (t_ok) {
+          if (d.skip_mode == VQVS_SKIP_IDENTITY) {
+            const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
+                                         : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
+            if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
+            else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
+            else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
+          }
+          d.out[((size_t)n * d.c_out + co) * d.t_out + t] = o;
+        } else {
+          o = 0.f;
+        }
+        v[j] = o;
+      }
+      if (d.stats_out) {
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+        const float s1 = column_sums32(v, lane);
+        const float s2 = column_sums32(sq, lane);
+        double* st = d.stats_out + ((size_t)n * d.c_out + co0 + lane) * 2;
+        atomicAdd(st, (double)s1);
+        atomicAdd(st + 1, (double)s2);
+      }
+    }
+    if ((g.n_tile & 31) && half == 0) {  // trailing 16 columns (tiny configurations only)
+      float v[16];
+      const int cbase = n_chunks32 * 32;
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + cbase, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = nt * g.n_tile + cbase + j;
+        float b = d.bias ? __ldg(d.bias + co) : 0.f;
+        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += __ldg(d.b_skip + co);
+        float o = v[j] + b;
+        if (t_ok) {
+          if (d.skip_mode == VQVS_SKIP_IDENTITY) {
+            const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
+                                         : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
+            if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
+            else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
+            else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
+          }
+          d.out[((size_t)n * d.c_out + co) * d.t_out + t] = o;
+        } else {
+          o = 0.f;
+        }
+        if (d.stats_out) {
+          const float s1 = warp_sum(o), s2 = warp_sum(o * o);
+          if (lane == 0) {
+            double* st = d.stats_out + ((size_t)n * d.c_out + co) * 2;
+            atomicAdd(st, (double)s1);
+            atomicAdd(st + 1, (double)s2);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TMA_WARP) {
+    // =========================== weight TMA ===========================
+    if (lane == 0) {
+      const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
+      for (int st = 0; st < total_stages; ++st) {
+        const int s = st % g.stages;
+        const uint32_t ph = (st / g.stages) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const bool is_skip = st >= g.main_stages;
+        const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
+        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
+        const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
+        const uint8_t* src = wimg + (is_skip ? (size_t)g.nkb_main * g.b_unit_main + (size_t)kb0 * g.b_unit_skip
+                                             : (size_t)kb0 * g.b_unit_main);
+        const uint32_t bytes = nk * unit;
+        mbar_expect_tx(full_b(s), bytes);
+        tma_bulk_g2s(smem_u32(stage0 + (size_t)s * g.stage_bytes + g.a_stage_bytes), src, bytes, full_b(s));
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(g.n_tile);
+      const uint32_t a_lbo = g.rows * 16, b_lbo = g.n_tile * 16;
+      uint32_t acc = 0;
+      for (int st = 0; st < total_stages; ++st) {
+        const int s = st % g.stages;
+        const uint32_t ph = (st / g.stages) & 1;
+        mbar_wait(full_a(s), ph);
+        mbar_wait(full_b(s), ph);
+        tc_fence_after();
+        const bool is_skip = st >= g.main_stages;
+        const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
+        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
+        const uint32_t a_base = smem_u32(stage0 + (size_t)s * g.stage_bytes);
+        const uint32_t b_base = a_base + g.a_stage_bytes;
+        const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
+        const int taps = is_skip ? 1 : ntaps;
+        for (int k = 0; k < nk; ++k) {
+          const uint32_t a_hi = a_base + k * g.a_kb_bytes;
+          const uint32_t a_lo = a_hi + g.rows * 32;
+          for (int tap = 0; tap < taps; ++tap) {
+            const uint32_t shift = is_skip ? 0u : (uint32_t)(tap * d.dilation * 16);
+            const uint32_t b_hi = b_base + k * unit + tap * (g.n_tile * 64);
+            const uint32_t b_lo = b_hi + g.n_tile * 32;
+            const uint64_t da_hi = make_desc(a_hi + shift, a_lbo, 128);
+            const uint64_t da_lo = make_desc(a_lo + shift, a_lbo, 128);
+            const uint64_t db_hi = make_desc(b_hi, b_lbo, 128);
+            const uint64_t db_lo = make_desc(b_lo, b_lbo, 128);
+            mma_bf16(tmem_base, da_hi, db_hi, idesc, acc);
+            acc = 1;
+            mma_bf16(tmem_base, da_lo, db_hi, idesc, 1);
+            mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
+          }
+        }
+        mma_commit(empty(s));
+      }
+      mma_commit(acc_full);
+    }
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, g.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// weight packer: fp32 [c_out, c_in, ksize] (+ [c_out, c_skip]) -> bf16 hi/lo smem image
+// ---------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ w_skip, int c_out, int c_in,
+                                    int ksize, int c_skip, Geo g, uint8_t* __restrict__ img) {
+  const long long n_main = (long long)c_out * c_in * ksize;
+  const long long total = n_main + (long long)c_out * c_skip;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float val;
+    int co, ci, tap;
+    bool skip = i >= n_main;
+    if (!skip) {
+      tap = (int)(i % ksize);
+      ci = (int)((i / ksize) % c_in);
+      co = (int)(i / ((long long)ksize * c_in));
+      val = w[i];
+    } else {
+      const long long j = i - n_main;
+      tap = 0;
+      ci = (int)(j % c_skip);
+      co = (int)(j / c_skip);
+      val = w_skip[j];
+    }
+    const int nt = co / g.n_tile, row = co - nt * g.n_tile;
+    const int kb = ci / KBLK, chunk = (ci % KBLK) / 8, e = ci % 8;
+    long long off = (long long)nt * g.per_tile_bytes;
+    if (!skip) off += (long long)kb * g.b_unit_main + (long long)tap * (g.n_tile * 64);
+    else off += (long long)g.nkb_main * g.b_unit_main + (long long)kb * g.b_unit_skip;
+    off += (long long)chunk * (g.n_tile * 16) + (long long)row * 16 + e * 2;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(img + off + g.n_tile * 32) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// self-test: D[128, n] = A[shift .. shift+128, :] * B^T through the production layout
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) selftest_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ dout, int n, int k, int row_shift, int variant) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t holder;
+  const int rows = TILE_M + row_shift;
+  const int nkb = k / KBLK;
+  const int a_kb = rows * 64, b_kb = n * 64;
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + nkb * a_kb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cols = 32;
+  while (cols < n) cols *= 2;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&holder), cols);
+  for (int i = threadIdx.x; i < nkb * 2 * rows; i += 128) {
+    const int q = i / rows, r = i - q * rows;
+    float v[8];
+    for (int e = 0; e < 8; ++e) v[e] = a[(size_t)r * k + q * 8 + e];
+    uint4 hi, lo;
+    split8(v, &hi, &lo);
+    uint8_t* p = a_s + (q >> 1) * a_kb + (q & 1) * (rows * 16);
+    *reinterpret_cast<uint4*>(p + r * 16) = hi;
+    *reinterpret_cast<uint4*>(p + rows * 32 + r * 16) = lo;
+  }
+  for (int i = threadIdx.x; i < nkb * 2 * n; i += 128) {
+    const int q = i / n, r = i - q * n;
+    float v[8];
+    for (int e = 0; e < 8; ++e) v[e] = b[(size_t)r * k + q * 8 + e];
+    uint4 hi, lo;
+    split8(v, &hi, &lo);
+    uint8_t* p = b_s + (q >> 1) * b_kb + (q & 1) * (n * 16);
+    *reinterpret_cast<uint4*>(p + r * 16) = hi;
+    *reinterpret_cast<uint4*>(p + n * 32 + r * 16) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = holder;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc(n);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t a_hi = smem_u32(a_s + kb * a_kb) + row_shift * 16, a_lo = a_hi + rows * 32;
+      const uint32_t b_hi = smem_u32(b_s + kb * b_kb), b_lo = b_hi + n * 32;
+      uint32_t a_l = rows * 16, a_sb = 128, b_l = n * 16, b_sb = 128;
+      if (variant == 1) { uint32_t t = a_l; a_l = a_sb; a_sb = t; t = b_l; b_l = b_sb; b_sb = t; }
+      mma_bf16(tmem_base, make_desc(a_hi, a_l, a_sb), make_desc(b_hi, b_l, b_sb), idesc, acc);
+      acc = 1;
+      if (variant != 2) {  // variant 2: hi*hi only (plain bf16) to separate layout bugs from split bugs
+        mma_bf16(tmem_base, make_desc(a_lo, a_l, a_sb), make_desc(b_hi, b_l, b_sb), idesc, 1);
+        mma_bf16(tmem_base, make_desc(a_hi, a_l, a_sb), make_desc(b_lo, b_l, b_sb), idesc, 1);
+      }
+    }
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int j = 0; j < 16; ++j) dout[(size_t)row * n + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, cols);
+  }
+}
+
+}  // namespace umma
+}  // namespace vqvs
+
+// =============================================================================
+// C ABI
+// =============================================================================
+using namespace vqvs;
+using vqvs::umma::Geo;
+
+static int umma_geo(const VqvsConv* d, Geo* g) {
+  const int c_skip = d->skip_mode == VQVS_SKIP_CONV1X1 ? d->s_a + d->s_b : 0;
+  if (!umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, g)) return 0;
+  if (d->c_a % umma::KBLK || d->c_b % umma::KBLK) return 0;
+  if (c_skip && (d->s_a % umma::KBLK || d->s_b % umma::KBLK)) return 0;
+  if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // float2 loads need even rows
+  return 1;
+}
+
+extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
+  Geo g;
+  return d && (d->ksize == 1 || d->ksize == 3) && d->dilation >= 1 && d->dilation <= 32 && umma_geo(d, &g);
+}
+
+extern "C" int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip) {
+  Geo g;
+  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, &g)) return -1;
+  return (int64_t)g.n_tiles * g.per_tile_bytes;
+}
+
+extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c_out, int c_in, int ksize, int c_skip,
+                                      void* packed, void* stream) {
+  Geo g;
+  VQVS_CHECK_ARG(w && packed && (c_skip == 0 || w_skip), "pack_conv_weights: null pointer");
+  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, &g), "pack_conv_weights: unsupported shape c_out=%d c_in=%d k=%d skip=%d",
+                 c_out, c_in, ksize, c_skip);
+  umma::pack_weights_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(w, w_skip, c_out, c_in, ksize, c_skip, g, (uint8_t*)packed);
+  VQVS_CHECK_LAUNCH("vqvs_pack_conv_weights");
+  return VQVS_OK;
+}
+
+static int require_sm100() {
+  static int cc = -1;
+  if (cc < 0) {
+    int c = 0, sms = 0;
+    if (vqvs_device_info(&c, &sms) != VQVS_OK) return VQVS_ECUDA;
+    cc = c;
+  }
+  if (cc / 10 != 10) {
+    set_error("tcgen05 path needs an sm_100-class device, found sm_%d", cc);
+    return VQVS_EARCH;
+  }
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
+  VQVS_CHECK_ARG(d != nullptr, "conv(umma): null descriptor");
+  int rc = require_sm100();
+  if (rc) return rc;
+  Geo g;
+  VQVS_CHECK_ARG((d->ksize == 1 || d->ksize == 3) && d->dilation >= 1 && d->dilation <= 32 && umma_geo(d, &g),
+                 "conv(umma): unsupported shape c_in=%d+%d c_out=%d k=%d dil=%d", d->c_a, d->c_b, d->c_out, d->ksize, d->dilation);
+  const int expect = d->resize == VQVS_RESIZE_DOWN2 ? d->t_in / 2 : d->resize == VQVS_RESIZE_UP2 ? d->t_in * 2 : d->t_in;
+  VQVS_CHECK_ARG(d->t_in > 0 && d->t_out == expect && d->batch > 0, "conv(umma): bad lengths");
+  VQVS_CHECK_ARG(d->xa && (d->c_b == 0 || d->xb) && d->out && d->w_packed, "conv(umma): null pointer");
+  VQVS_CHECK_ARG(!d->act || (d->scale && d->shift), "conv(umma): act=1 needs scale/shift");
+  if (d->skip_mode != VQVS_SKIP_NONE) {
+    VQVS_CHECK_ARG(d->sa && d->s_a > 0 && (d->s_b == 0 || d->sb), "conv(umma): skip sources missing");
+    const int sexp = d->skip_resize == VQVS_RESIZE_DOWN2 ? d->t_skip / 2 : d->skip_resize == VQVS_RESIZE_UP2 ? d->t_skip * 2 : d->t_skip;
+    VQVS_CHECK_ARG(d->t_skip > 0 && sexp == d->t_out, "conv(umma): skip length mismatch");
+    VQVS_CHECK_ARG(d->skip_resize != VQVS_RESIZE_DOWN2 || (d->t_skip & 1) == 0, "conv(umma): odd skip length with pooling");
+    if (d->skip_mode == VQVS_SKIP_IDENTITY)
+      VQVS_CHECK_ARG(d->s_a + d->s_b == d->c_out, "conv(umma): identity skip channel mismatch");
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return VQVS_ECUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(d->t_out, umma::TILE_M), g.n_tiles, d->batch);
+  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(*d, g);
+  VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_umma_selftest(const float* a, const float* b, float* dout, int n, int k, int row_shift, int variant,
+                                  void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  VQVS_CHECK_ARG(a && b && dout && n >= 16 && n <= 256 && n % 16 == 0 && k > 0 && k % 16 == 0 && row_shift >= 0,
+                 "umma_selftest: bad arguments");
+  const size_t smem = (size_t)(k / 16) * ((128 + row_shift) * 64 + n * 64);
+  VQVS_CHECK_ARG(smem <= 200 * 1024, "umma_selftest: problem too large for one CTA");
+  cudaError_t e = cudaFuncSetAttribute(umma::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    set_error("umma_selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return VQVS_ECUDA;
+  }
+  umma::selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, dout, n, k, row_shift, variant);
+  VQVS_CHECK_LAUNCH("vqvs_umma_selftest");
+  return VQVS_OK;
+}
