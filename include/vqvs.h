@@ -257,6 +257,9 @@ typedef struct VqvsOp {
 } VqvsOp;
 /* Returns 0, or the first failing op's status (message names the op index). */
 int vqvs_run(const VqvsOp* ops, int n_ops, void* stream);
+/* Same, bracketing every op with CUDA events on `stream`; host_ms[i] receives op i's device time
+ * in milliseconds (synchronises the stream at the end; measurement aid for bench.py). */
+int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 
 /* tcgen05 self-test: runs D[128,n] = A[128,k] * B[n,k]^T through the exact smem layout,
  * descriptors and TMEM read-back used by vqvs_conv1d_umma, with A rows shifted by `row_shift`.

@@ -37,11 +37,38 @@ extern "C" int vqvs_device_info(int* cc, int* sm_count) {
   return VQVS_OK;
 }
 
-extern "C" int vqvs_run(const VqvsOp* ops, int n_ops, void* stream) {
+static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev);
+
+extern "C" int vqvs_run(const VqvsOp* ops, int n_ops, void* stream) { return run_impl(ops, n_ops, stream, nullptr); }
+
+extern "C" int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms) {
+  if (!ops || n_ops <= 0 || !host_ms) {
+    vqvs::set_error("vqvs_run_timed: bad arguments");
+    return VQVS_EINVAL;
+  }
+  cudaEvent_t* ev = new cudaEvent_t[n_ops + 1];
+  for (int i = 0; i <= n_ops; ++i) cudaEventCreate(&ev[i]);
+  int rc = run_impl(ops, n_ops, stream, ev);
+  if (rc == VQVS_OK) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      vqvs::set_error("vqvs_run_timed: %s", cudaGetErrorString(e));
+      rc = VQVS_ECUDA;
+    } else {
+      for (int i = 0; i < n_ops; ++i) cudaEventElapsedTime(&host_ms[i], ev[i], ev[i + 1]);
+    }
+  }
+  for (int i = 0; i <= n_ops; ++i) cudaEventDestroy(ev[i]);
+  delete[] ev;
+  return rc;
+}
+
+static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev) {
   if (!ops || n_ops < 0) {
     vqvs::set_error("vqvs_run: bad program");
     return VQVS_EINVAL;
   }
+  if (ev) cudaEventRecord(ev[0], (cudaStream_t)stream);
   for (int i = 0; i < n_ops; ++i) {
     int rc = VQVS_OK;
     const void* p = ops[i].desc;
@@ -74,6 +101,7 @@ extern "C" int vqvs_run(const VqvsOp* ops, int n_ops, void* stream) {
       vqvs::set_error("vqvs_run: op %d (kind %d) failed: %s", i, ops[i].kind, msg);
       return rc;
     }
+    if (ev) cudaEventRecord(ev[i + 1], (cudaStream_t)stream);
   }
   return VQVS_OK;
 }

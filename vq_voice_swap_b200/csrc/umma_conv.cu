@@ -700,6 +700,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
+      (void)cudaGetLastError();
       set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return VQVS_ECUDA;
     }
@@ -719,8 +720,9 @@ extern "C" int vqvs_umma_selftest(const float* a, const float* b, float* dout, i
                  "umma_selftest: bad arguments");
   const size_t smem = (size_t)(k / 16) * ((128 + row_shift) * 64 + n * 64);
   VQVS_CHECK_ARG(smem <= 200 * 1024, "umma_selftest: problem too large for one CTA");
-  cudaError_t e = cudaFuncSetAttribute(umma::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(umma::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
+    (void)cudaGetLastError();
     set_error("umma_selftest: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return VQVS_ECUDA;
   }
