@@ -18,7 +18,9 @@
 //   store coalesced along time, and reduce per-channel (sum, sumsq) for the next GroupNorm with a
 //   transposing shuffle butterfly + fp64 atomics.
 // The optional 1x1 skip conv (reference models/unet.py:265-271) is extra K blocks over the raw input.
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -46,14 +48,21 @@ struct Geo {
   int a_kb_bytes;           // A bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
   int b_unit_main;          // W bytes per main K block: ksize taps x hi/lo x 2 chunks x n_tile rows x 16 B
   int b_unit_skip;          // W bytes per skip K block
-  int stage_bytes;          // kbs * (a_kb_bytes + b_unit_main)
-  int a_stage_bytes;
-  int param_bytes;          // scale/shift staging
+  int raw_kb_bytes;         // raw fp32 staging per K block (TMA mode): 16 channels x widest box
+  int stage_bytes;          // kbs * (raw_kb_bytes + a_kb_bytes + b_unit_main)
+  int raw_stage_bytes, a_stage_bytes;
+  int param_bytes;          // (scale, shift) pairs + bias staging
   long long per_tile_bytes; // packed image bytes per N tile
   int smem_bytes;
+  // TMA activation boxes, in SOURCE coordinates relative to the tile origin
+  int tma;                  // 1: raw activations arrive by cp.async.bulk.tensor into the staging ring
+  int main_box_w, main_boxes, main_origin_mul, main_origin_off;  // box x0 = t0*mul/2 + off (mul: 1=up2, 2=none, 4=down2)
+  int skip_box_w, skip_origin_mul;
 };
 
-static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, Geo* g) {
+__host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
+
+static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
   g->n_tiles = (c_out + 255) / 256;
   if (c_out % g->n_tiles) return false;
@@ -66,14 +75,38 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, G
   g->a_kb_bytes = g->rows * 64;
   g->b_unit_main = ksize * g->n_tile * 64;
   g->b_unit_skip = g->n_tile * 64;
-  int per_kb = g->a_kb_bytes + g->b_unit_main;
-  int kbs = (36 * 1024) / per_kb;
+  g->tma = tma ? 1 : 0;
+  g->raw_kb_bytes = 0;
+  g->main_box_w = g->main_boxes = g->main_origin_mul = g->main_origin_off = g->skip_box_w = g->skip_origin_mul = 0;
+  if (tma) {
+    const int off = round_up4(g->pad);
+    if (resize == VQVS_RESIZE_NONE) {          // source [t0 - off, t0 + 128 + off)
+      g->main_box_w = TILE_M + 2 * off; g->main_boxes = 1; g->main_origin_mul = 2; g->main_origin_off = -off;
+    } else if (resize == VQVS_RESIZE_UP2) {    // conv [t0-pad, t0+128+pad) -> source [t0/2 - 4, t0/2 + 68)
+      if (g->pad > 4) return false;
+      g->main_box_w = TILE_M / 2 + 8; g->main_boxes = 1; g->main_origin_mul = 1; g->main_origin_off = -4;
+    } else {                                   // source [2*t0 - 4, 2*t0 + 260): two boxes of 132
+      if (g->pad > 2) return false;
+      g->main_box_w = TILE_M + 4; g->main_boxes = 2; g->main_origin_mul = 4; g->main_origin_off = -4;
+    }
+    int widest = g->main_box_w * g->main_boxes;
+    if (c_skip) {
+      g->skip_box_w = skip_resize == VQVS_RESIZE_NONE ? TILE_M : skip_resize == VQVS_RESIZE_UP2 ? TILE_M / 2 : 2 * TILE_M;
+      g->skip_origin_mul = skip_resize == VQVS_RESIZE_NONE ? 2 : skip_resize == VQVS_RESIZE_UP2 ? 1 : 4;
+      if (g->skip_box_w > widest) widest = g->skip_box_w;
+    }
+    if (g->main_box_w > 256 || g->skip_box_w > 256) return false;
+    g->raw_kb_bytes = KBLK * widest * 4;
+  }
+  const int per_kb = g->raw_kb_bytes + g->a_kb_bytes + g->b_unit_main;
+  int kbs = (40 * 1024) / per_kb;
   g->kbs = kbs < 1 ? 1 : (kbs > 4 ? 4 : kbs);
   g->stage_bytes = g->kbs * per_kb;
+  g->raw_stage_bytes = g->kbs * g->raw_kb_bytes;
   g->a_stage_bytes = g->kbs * g->a_kb_bytes;
-  g->param_bytes = ((2 * c_in * 4) + 127) / 128 * 128;
+  g->param_bytes = ((2 * c_in * 4 + g->n_tile * 4) + 127) / 128 * 128;
   const int fixed = SMEM_HEADER + g->param_bytes;
-  int stages = (110 * 1024 - fixed) / g->stage_bytes;  // two CTAs per SM when it fits
+  int stages = (112 * 1024 - fixed) / g->stage_bytes;  // two CTAs per SM when it fits
   if (stages < 2) stages = (225 * 1024 - fixed) / g->stage_bytes;
   if (stages < 2) return false;
   g->stages = stages > MAX_STAGES ? MAX_STAGES : stages;
@@ -189,17 +222,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // ---------------------------------------------------------------------------
 // prologue math
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
 // max |error| 4.2e-7 over [-12, 12] in fp32, tighter than ATen's own fp32 GELU (1.2e-6).
+// Two MUFU ops (rcp, ex2) + 11 FP32 ops per element.
 __device__ __forceinline__ float gelu_as(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-z * z * 1.4426950408889634f);
-  const float half_erfc = 0.5f * p * t * e;  // 0.5*erfc(|x|/sqrt2)
+  const float e = ex2_approx(z * z * -1.4426950408889634f);
+  const float half_erfc = (0.5f * t) * (p * e);  // 0.5*erfc(|x|/sqrt2)
   const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   return x * phi;
 }
@@ -210,14 +254,31 @@ __device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float r0 = v[2 * i] - __low2float(hb);
-    const float r1 = v[2 * i + 1] - __high2float(hb);
-    const __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
     h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
     l[i] = *reinterpret_cast<const uint32_t*>(&lb);
   }
   *hi = make_uint4(h[0], h[1], h[2], h[3]);
   *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void store_rows(const float* v, uint8_t* a_hi, uint8_t* a_lo, int row) {
+  uint4 hi, lo;
+  split8(v, &hi, &lo);
+  *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
+  *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+}
+
+// (scale, shift) for 8 consecutive channels: four float4 = {sc0, sh0, sc1, sh1} ...
+__device__ __forceinline__ void affine_gelu8(float* v, const float4* ss) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 p = ss[i];
+    v[2 * i] = gelu_as(fmaf(v[2 * i], p.x, p.y));
+    v[2 * i + 1] = gelu_as(fmaf(v[2 * i + 1], p.z, p.w));
+  }
 }
 
 struct Src {
@@ -226,9 +287,9 @@ struct Src {
   int c_a, c_b, t_in, t_conv, resize;
 };
 
-// Stage one 16-B A element: 8 consecutive channels [c8, c8+8) at conv-input position tc -> row `row`.
-__device__ __forceinline__ void produce_item(const Src& s, int n, int c8, int tc, bool act, const float* sc,
-                                             const float* sh, uint8_t* a_hi, uint8_t* a_lo, int row) {
+// Direct mode (no TMA: lengths not a multiple of 4): 8 channels [c8, c8+8) at conv-input position tc.
+__device__ __forceinline__ void produce_direct(const Src& s, int n, int c8, int tc, bool act, const float4* ss,
+                                               uint8_t* a_hi, uint8_t* a_lo, int row) {
   float v[8];
   if (tc < 0 || tc >= s.t_conv) {
 #pragma unroll
@@ -237,32 +298,26 @@ __device__ __forceinline__ void produce_item(const Src& s, int n, int c8, int tc
     const float* base = c8 < s.c_a ? s.a + ((size_t)n * s.c_a + c8) * s.t_in
                                    : s.b + ((size_t)n * s.c_b + (c8 - s.c_a)) * s.t_in;
     if (s.resize == VQVS_RESIZE_DOWN2) {
-      float2 x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __ldg(reinterpret_cast<const float2*>(base + (size_t)e * s.t_in + 2 * tc));
+      float w[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        if (act) {
-          const float a0 = gelu_as(fmaf(x[e].x, sc[e], sh[e]));
-          const float a1 = gelu_as(fmaf(x[e].y, sc[e], sh[e]));
-          v[e] = 0.5f * (a0 + a1);
-        } else {
-          v[e] = 0.5f * (x[e].x + x[e].y);
-        }
+        v[e] = __ldg(base + (size_t)e * s.t_in + 2 * tc);
+        w[e] = __ldg(base + (size_t)e * s.t_in + 2 * tc + 1);
       }
+      if (act) {
+        affine_gelu8(v, ss);
+        affine_gelu8(w, ss);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.5f * (v[e] + w[e]);
     } else {
       const int ts = s.resize == VQVS_RESIZE_UP2 ? (tc >> 1) : tc;
-      float x[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __ldg(base + (size_t)e * s.t_in + ts);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = act ? gelu_as(fmaf(x[e], sc[e], sh[e])) : x[e];
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(base + (size_t)e * s.t_in + ts);
+      if (act) affine_gelu8(v, ss);
     }
   }
-  uint4 hi, lo;
-  split8(v, &hi, &lo);
-  *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
-  *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+  store_rows(v, a_hi, a_lo, row);
 }
 
 // Transposing butterfly: every lane holds v[0..31] (one row, 32 columns); afterwards lane l holds
@@ -284,39 +339,67 @@ __device__ __forceinline__ float column_sums32(float* v, int lane) {
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g) {
+// TMA tensor load of one [16 channels x box_w positions] fp32 box (SASS: UTMALDG); out-of-range
+// positions are zero-filled by the hardware.
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
+                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
+                 const Geo g) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars[0..3] full_a, [4..7] full_b, [8..11] empty, [12] acc_full
+  // bars[0..3] full_ld (TMA: raw activations + weights), [4..7] full_a (operand tile written),
+  // [8..11] empty (MMAs of the stage retired), [12] acc_full
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 13 * 8);
-  float* s_scale = reinterpret_cast<float*>(smem + SMEM_HEADER);
   const int c_in = d.c_a + d.c_b;
-  float* s_shift = s_scale + c_in;
+  float2* s_ss = reinterpret_cast<float2*>(smem + SMEM_HEADER);
+  float* s_bias = reinterpret_cast<float*>(s_ss + c_in);
   uint8_t* stage0 = smem + SMEM_HEADER + g.param_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.z, nt = blockIdx.y, t0 = blockIdx.x * TILE_M;
   const uint32_t bar0 = smem_u32(bars);
-  auto full_a = [&](int s) { return bar0 + 8u * s; };
-  auto full_b = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto empty = [&](int s) { return bar0 + 8u * (8 + s); };
   const uint32_t acc_full = bar0 + 8u * 12;
+#define FULL_LD(s) (bar0 + 8u * (s))
+#define FULL_A(s) (bar0 + 8u * (4 + (s)))
+#define EMPTY(s) (bar0 + 8u * (8 + (s)))
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(full_a(s), PRODUCER_THREADS);
-      mbar_init(full_b(s), 1);
-      mbar_init(empty(s), 1);
+      mbar_init(FULL_LD(s), 1);
+      mbar_init(FULL_A(s), PRODUCER_THREADS);
+      mbar_init(EMPTY(s), 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_holder), g.tmem_cols);
-  if (d.act) {
-    for (int i = threadIdx.x; i < c_in; i += THREADS) {
-      s_scale[i] = d.scale[(size_t)n * c_in + i];
-      s_shift[i] = d.shift[(size_t)n * c_in + i];
+  if (warp == TMA_WARP && lane == 0 && g.tma) {
+    tma_prefetch_desc(&tm_xa);
+    if (d.c_b) tma_prefetch_desc(&tm_xb);
+    if (g.nkb_skip) {
+      tma_prefetch_desc(&tm_sa);
+      if (d.s_b) tma_prefetch_desc(&tm_sb);
     }
+  }
+  if (d.act) {
+    for (int i = threadIdx.x; i < c_in; i += THREADS)
+      s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
+  }
+  for (int i = threadIdx.x; i < g.n_tile; i += THREADS) {
+    const int co = nt * g.n_tile + i;
+    float b = d.bias ? d.bias[co] : 0.f;
+    if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
+    s_bias[i] = b;
   }
   tc_fence_before();
   __syncthreads();
@@ -324,51 +407,145 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
   const uint32_t tmem_base = *tmem_holder;
 
   const int total_stages = g.main_stages + g.skip_stages;
-  const int ntaps = d.ksize;
 
   if (warp < PRODUCER_WARPS) {
-    // =========================== producers ===========================
+    // =========================== operand producers ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     for (int st = 0; st < total_stages; ++st) {
       const int s = st % g.stages;
       const uint32_t ph = (st / g.stages) & 1;
-      mbar_wait(empty(s), ph ^ 1);
-      uint8_t* a_stage = stage0 + (size_t)s * g.stage_bytes;
+      mbar_wait(EMPTY(s), ph ^ 1);
+      uint8_t* stage = stage0 + (size_t)s * g.stage_bytes;
+      uint8_t* a_stage = stage + g.raw_stage_bytes;
       const bool is_skip = st >= g.main_stages;
       const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
-      const int kb_end = is_skip ? g.nkb_skip : g.nkb_main;
-      const int nk = min(g.kbs, kb_end - kb0);
-      const Src& src = is_skip ? skip_src : main_src;
+      const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
       const bool act = !is_skip && d.act;
       const int pad = is_skip ? 0 : g.pad;
-      // main rows: one item = (8-channel chunk q, position m)
-      for (int i = threadIdx.x; i < nk * 2 * TILE_M; i += PRODUCER_THREADS) {
-        const int q = i >> 7, m = i & (TILE_M - 1);
-        const int c8 = kb0 * KBLK + q * 8;
-        uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-        uint8_t* a_lo = a_hi + g.rows * 32;
-        produce_item(src, n, c8, t0 + m, act, s_scale + c8, s_shift + c8, a_hi, a_lo, pad + m);
-      }
-      // halo rows [0,pad) and [128+pad, 128+2*pad)
-      const int n_halo = nk * 2 * 2 * pad;
-      for (int i = threadIdx.x; i < n_halo; i += PRODUCER_THREADS) {
-        const int q = i / (2 * pad), e = i - q * (2 * pad);
-        const int row = e < pad ? e : TILE_M + e;
-        const int c8 = kb0 * KBLK + q * 8;
-        uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-        uint8_t* a_lo = a_hi + g.rows * 32;
-        produce_item(src, n, c8, t0 - pad + row, act, s_scale + c8, s_shift + c8, a_hi, a_lo, row);
+      const int resize = is_skip ? d.skip_resize : d.resize;
+      const int t_src = is_skip ? d.t_skip : d.t_in;
+      if (!g.tma) {
+        const Src& src = is_skip ? skip_src : main_src;
+        for (int i = threadIdx.x; i < nk * 2 * TILE_M; i += PRODUCER_THREADS) {
+          const int q = i >> 7, m = i & (TILE_M - 1);
+          const int c8 = kb0 * KBLK + q * 8;
+          uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+          produce_direct(src, n, c8, t0 + m, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, pad + m);
+        }
+        const int n_halo = nk * 2 * 2 * pad;
+        for (int i = threadIdx.x; i < n_halo; i += PRODUCER_THREADS) {
+          const int q = i / (2 * pad), e = i - q * (2 * pad);
+          const int row = e < pad ? e : TILE_M + e;
+          const int c8 = kb0 * KBLK + q * 8;
+          uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+          produce_direct(src, n, c8, t0 - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
+        }
+      } else {
+        mbar_wait(FULL_LD(s), ph);  // raw fp32 boxes have landed
+        const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
+        const int mul = is_skip ? g.skip_origin_mul : g.main_origin_mul;
+        const int x0 = (t0 * mul) / 2 + (is_skip ? 0 : g.main_origin_off);  // source position of raw column 0
+        const int tcs = t0 - pad;                                           // conv position of row 0
+        const int rows = TILE_M + 2 * pad;
+        if (resize == VQVS_RESIZE_UP2) {
+          // one item = 8 channels x one SOURCE position -> two output rows (GELU evaluated once)
+          const int first = tcs >> 1;
+          const int nsrc = ((tcs + rows - 1) >> 1) - first + 1;
+          for (int i = threadIdx.x; i < nk * 2 * nsrc; i += PRODUCER_THREADS) {
+            const int q = i / nsrc, j = i - q * nsrc;
+            const int ts = first + j;
+            const float* raw = reinterpret_cast<const float*>(stage + (q >> 1) * g.raw_kb_bytes) + ((q & 1) * 8) * box_w + (ts - x0);
+            float v[8];
+            if (ts >= 0 && ts < t_src) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = raw[e * box_w];
+              if (act) affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+            uint4 hi, lo;
+            split8(v, &hi, &lo);
+            uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+            uint8_t* a_lo = a_hi + g.rows * 32;
+            const int r0 = 2 * ts - tcs;
+            if (r0 >= 0) {
+              *reinterpret_cast<uint4*>(a_hi + r0 * 16) = hi;
+              *reinterpret_cast<uint4*>(a_lo + r0 * 16) = lo;
+            }
+            if (r0 + 1 < rows) {
+              *reinterpret_cast<uint4*>(a_hi + (r0 + 1) * 16) = hi;
+              *reinterpret_cast<uint4*>(a_lo + (r0 + 1) * 16) = lo;
+            }
+          }
+        } else {
+          const bool down = resize == VQVS_RESIZE_DOWN2;
+          const int boxes = is_skip ? 1 : g.main_boxes;
+          // rows [0, rows) of every 8-channel chunk; the few halo rows beyond 128 go to one rotating warp
+          const int per_chunk_main = TILE_M, n_extra = rows - TILE_M;
+          for (int pass = 0; pass < 2; ++pass) {
+            const int count = nk * 2 * (pass == 0 ? per_chunk_main : n_extra);
+            if (pass == 1 && (count == 0 || warp != (st & (PRODUCER_WARPS - 1)))) break;
+            for (int i = (pass == 0 ? (int)threadIdx.x : lane); i < count; i += (pass == 0 ? PRODUCER_THREADS : 32)) {
+              int q, row;
+              if (pass == 0) {
+                q = i >> 7;
+                row = i & (TILE_M - 1);
+              } else {
+                q = i / n_extra;
+                row = TILE_M + (i - q * n_extra);
+              }
+              const int tc = tcs + row;
+              const float* raw_k = reinterpret_cast<const float*>(stage + (q >> 1) * g.raw_kb_bytes);
+              float v[8];
+              if (tc >= 0 && tc < d.t_out) {
+                if (!down) {
+                  const float* raw = raw_k + ((q & 1) * 8) * box_w + (tc - x0);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = raw[e * box_w];
+                  if (act) affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
+                } else {
+                  int col = 2 * tc - x0;
+                  const float* raw = raw_k;
+                  if (boxes == 2 && col >= box_w) {
+                    col -= box_w;
+                    raw += KBLK * box_w;
+                  }
+                  raw += ((q & 1) * 8) * box_w + col;
+                  float w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float2 p = *reinterpret_cast<const float2*>(raw + e * box_w);
+                    v[e] = p.x;
+                    w[e] = p.y;
+                  }
+                  if (act) {
+                    affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
+                    affine_gelu8(w, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
+                  }
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = 0.5f * (v[e] + w[e]);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+              }
+              uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
+              store_rows(v, a_hi, a_hi + g.rows * 32, row);
+            }
+          }
+        }
       }
       fence_proxy_async();
-      mbar_arrive(full_a(s));
+      mbar_arrive(FULL_A(s));
     }
 
     // =========================== epilogue ===========================
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int quarter = warp & 3;           // TMEM lanes [32*quarter, +32) belong to this warp
-    const int half = warp >> 2;             // the two warps of a quarter split the columns
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = warp >> 2;    // the two warps of a quarter split the columns
     const int row = quarter * 32 + lane;
     const int t = t0 + row;
     const bool t_ok = t < d.t_out;
@@ -377,21 +554,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, v);
       const int co0 = nt * g.n_tile + ch * 32;
+      float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int co = co0 + j;
-        float b = d.bias ? __ldg(d.bias + co) : 0.f;
-        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += __ldg(d.b_skip + co);
-        float o = v[j] + b;
+        float o = v[j] + s_bias[ch * 32 + j];
         if (t_ok) {
           if (d.skip_mode == VQVS_SKIP_IDENTITY) {
+            const int co = co0 + j;
             const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
                                          : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
             if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
             else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
             else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
           }
-          d.out[((size_t)n * d.c_out + co) * d.t_out + t] = o;
+          outp[(size_t)j * d.t_out] = o;
         } else {
           o = 0.f;
         }
@@ -415,9 +591,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int co = nt * g.n_tile + cbase + j;
-        float b = d.bias ? __ldg(d.bias + co) : 0.f;
-        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += __ldg(d.b_skip + co);
-        float o = v[j] + b;
+        float o = v[j] + s_bias[cbase + j];
         if (t_ok) {
           if (d.skip_mode == VQVS_SKIP_IDENTITY) {
             const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
@@ -442,22 +616,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
     }
     tc_fence_before();
   } else if (warp == TMA_WARP) {
-    // =========================== weight TMA ===========================
+    // =========================== TMA issuer: raw activation boxes + weight image ===========================
     if (lane == 0) {
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
       for (int st = 0; st < total_stages; ++st) {
         const int s = st % g.stages;
         const uint32_t ph = (st / g.stages) & 1;
-        mbar_wait(empty(s), ph ^ 1);
+        mbar_wait(EMPTY(s), ph ^ 1);
         const bool is_skip = st >= g.main_stages;
         const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
         const uint8_t* src = wimg + (is_skip ? (size_t)g.nkb_main * g.b_unit_main + (size_t)kb0 * g.b_unit_skip
                                              : (size_t)kb0 * g.b_unit_main);
-        const uint32_t bytes = nk * unit;
-        mbar_expect_tx(full_b(s), bytes);
-        tma_bulk_g2s(smem_u32(stage0 + (size_t)s * g.stage_bytes + g.a_stage_bytes), src, bytes, full_b(s));
+        uint8_t* stage = stage0 + (size_t)s * g.stage_bytes;
+        const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
+        const int boxes = is_skip ? 1 : g.main_boxes;
+        uint32_t bytes = nk * unit;
+        if (g.tma) bytes += nk * boxes * KBLK * box_w * 4;
+        mbar_expect_tx(FULL_LD(s), bytes);
+        if (g.tma) {
+          const int mul = is_skip ? g.skip_origin_mul : g.main_origin_mul;
+          const int x0 = (t0 * mul) / 2 + (is_skip ? 0 : g.main_origin_off);
+          const int ca = is_skip ? d.s_a : d.c_a, cb = is_skip ? d.s_b : d.c_b;
+          for (int k = 0; k < nk; ++k) {
+            const int c16 = (kb0 + k) * KBLK;
+            const CUtensorMap* map = c16 < ca ? (is_skip ? &tm_sa : &tm_xa) : (is_skip ? &tm_sb : &tm_xb);
+            const int rowc = c16 < ca ? n * ca + c16 : n * cb + (c16 - ca);
+            for (int b = 0; b < boxes; ++b)
+              tma_box_2d(smem_u32(stage + k * g.raw_kb_bytes + b * (KBLK * box_w * 4)), map, x0 + b * box_w, rowc, FULL_LD(s));
+          }
+        }
+        tma_bulk_g2s(smem_u32(stage + g.raw_stage_bytes + g.a_stage_bytes), src, nk * unit, FULL_LD(s));
       }
     }
   } else {
@@ -469,16 +659,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
       for (int st = 0; st < total_stages; ++st) {
         const int s = st % g.stages;
         const uint32_t ph = (st / g.stages) & 1;
-        mbar_wait(full_a(s), ph);
-        mbar_wait(full_b(s), ph);
+        mbar_wait(FULL_LD(s), ph);
+        mbar_wait(FULL_A(s), ph);
         tc_fence_after();
         const bool is_skip = st >= g.main_stages;
         const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-        const uint32_t a_base = smem_u32(stage0 + (size_t)s * g.stage_bytes);
+        const uint32_t a_base = smem_u32(stage0 + (size_t)s * g.stage_bytes + g.raw_stage_bytes);
         const uint32_t b_base = a_base + g.a_stage_bytes;
         const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
-        const int taps = is_skip ? 1 : ntaps;
+        const int taps = is_skip ? 1 : d.ksize;
         for (int k = 0; k < nk; ++k) {
           const uint32_t a_hi = a_base + k * g.a_kb_bytes;
           const uint32_t a_lo = a_hi + g.rows * 32;
@@ -496,7 +686,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
             mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
           }
         }
-        mma_commit(empty(s));
+        mma_commit(EMPTY(s));
       }
       mma_commit(acc_full);
     }
@@ -506,6 +696,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(VqvsConv d, Geo g
     tc_fence_after();
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
+#undef FULL_LD
+#undef FULL_A
+#undef EMPTY
 }
 
 // ---------------------------------------------------------------------------
@@ -632,13 +825,23 @@ __global__ void __launch_bounds__(128) selftest_kernel(const float* __restrict__
 using namespace vqvs;
 using vqvs::umma::Geo;
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// TMA needs 16-B aligned bases and row pitches (length % 4 == 0); otherwise the kernel reads directly.
+static bool tma_eligible(const VqvsConv* d) {
+  if (d->t_in % 4 || !aligned16(d->xa) || (d->c_b && !aligned16(d->xb))) return false;
+  if (d->skip_mode == VQVS_SKIP_CONV1X1 && (d->t_skip % 4 || !aligned16(d->sa) || (d->s_b && !aligned16(d->sb)))) return false;
+  return true;
+}
+
 static int umma_geo(const VqvsConv* d, Geo* g) {
   const int c_skip = d->skip_mode == VQVS_SKIP_CONV1X1 ? d->s_a + d->s_b : 0;
-  if (!umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, g)) return 0;
   if (d->c_a % umma::KBLK || d->c_b % umma::KBLK) return 0;
   if (c_skip && (d->s_a % umma::KBLK || d->s_b % umma::KBLK)) return 0;
-  if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // float2 loads need even rows
-  return 1;
+  if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // paired loads need even rows
+  const bool tma = tma_eligible(d);
+  if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g)) return 1;
+  return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g) ? 1 : 0;
 }
 
 extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
@@ -648,7 +851,7 @@ extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
 
 extern "C" int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip) {
   Geo g;
-  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, &g)) return -1;
+  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g)) return -1;
   return (int64_t)g.n_tiles * g.per_tile_bytes;
 }
 
@@ -656,8 +859,8 @@ extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c
                                       void* packed, void* stream) {
   Geo g;
   VQVS_CHECK_ARG(w && packed && (c_skip == 0 || w_skip), "pack_conv_weights: null pointer");
-  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, &g), "pack_conv_weights: unsupported shape c_out=%d c_in=%d k=%d skip=%d",
-                 c_out, c_in, ksize, c_skip);
+  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g),
+                 "pack_conv_weights: unsupported shape c_out=%d c_in=%d k=%d skip=%d", c_out, c_in, ksize, c_skip);
   umma::pack_weights_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(w, w_skip, c_out, c_in, ksize, c_skip, g, (uint8_t*)packed);
   VQVS_CHECK_LAUNCH("vqvs_pack_conv_weights");
   return VQVS_OK;
@@ -673,6 +876,44 @@ static int require_sm100() {
   if (cc / 10 != 10) {
     set_error("tcgen05 path needs an sm_100-class device, found sm_%d", cc);
     return VQVS_EARCH;
+  }
+  return VQVS_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// [rows = batch*channels][t] fp32 tensor, boxes of 16 rows x box_w positions, zero fill outside.
+static int encode_map(CUtensorMap* m, const float* base, int rows, int t, int box_w) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("conv(umma): cuTensorMapEncodeTiled is not available from the driver");
+    return VQVS_ECUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)t, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)t * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)umma::KBLK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv(umma): cuTensorMapEncodeTiled failed with CUresult %d (rows=%d t=%d box=%d)", (int)r, rows, t, box_w);
+    return VQVS_ECUDA;
   }
   return VQVS_OK;
 }
@@ -706,8 +947,18 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     }
     attr_done = true;
   }
+  alignas(64) CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  if (g.tma) {
+    if ((rc = encode_map(&maps[0], d->xa, d->batch * d->c_a, d->t_in, g.main_box_w))) return rc;
+    if (d->c_b && (rc = encode_map(&maps[1], d->xb, d->batch * d->c_b, d->t_in, g.main_box_w))) return rc;
+    if (g.nkb_skip) {
+      if ((rc = encode_map(&maps[2], d->sa, d->batch * d->s_a, d->t_skip, g.skip_box_w))) return rc;
+      if (d->s_b && (rc = encode_map(&maps[3], d->sb, d->batch * d->s_b, d->t_skip, g.skip_box_w))) return rc;
+    }
+  }
   dim3 grid(ceil_div(d->t_out, umma::TILE_M), g.n_tiles, d->batch);
-  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(*d, g);
+  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }
