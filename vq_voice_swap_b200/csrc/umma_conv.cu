@@ -499,7 +499,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               const int tc = tcs + row;
               const float* raw_k = reinterpret_cast<const float*>(stage + (q >> 1) * g.raw_kb_bytes);
               float v[8];
-              if (tc >= 0 && tc < d.t_out) {
+              if (tc >= 0 && tc < d.t_out && !(d.reserved_ & 8)) {
                 if (!down) {
                   const float* raw = raw_k + ((q & 1) * 8) * box_w + (tc - x0);
 #pragma unroll
@@ -551,6 +551,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const bool t_ok = t < d.t_out;
     const int n_chunks32 = g.n_tile / 32;
     for (int ch = half; ch < n_chunks32; ch += 2) {
+      if (d.reserved_ & 16) break;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, v);
       const int co0 = nt * g.n_tile + ch * 32;
@@ -567,13 +568,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
             else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
           }
-          outp[(size_t)j * d.t_out] = o;
+          if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
         } else {
           o = 0.f;
         }
         v[j] = o;
       }
-      if (d.stats_out) {
+      if (d.stats_out && !(d.reserved_ & 1)) {
         float sq[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -680,6 +681,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             const uint64_t da_lo = make_desc(a_lo + shift, a_lbo, 128);
             const uint64_t db_hi = make_desc(b_hi, b_lbo, 128);
             const uint64_t db_lo = make_desc(b_lo, b_lbo, 128);
+            if (d.reserved_ & 4) continue;
             mma_bf16(tmem_base, da_hi, db_hi, idesc, acc);
             acc = 1;
             mma_bf16(tmem_base, da_lo, db_hi, idesc, 1);

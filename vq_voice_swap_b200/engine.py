@@ -277,6 +277,7 @@ def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, 
         if skip_proj is not None:
             d.w_skip, d.b_skip = L.ptr(skip_proj.weight), L.ptr(skip_proj.bias)
     d.w_packed = L.ptr(packed)
+    d.reserved_ = int(os.environ.get("VQVS_DEBUG_FLAGS", "0"))  # kernel ablation switches (profiling only)
     d.out, d.stats_out = out.ptr, out.stats_ptr
     kind = L.OP_CONV_SIMT
     if plan.backend == "umma" and packed is not None and L.load().vqvs_conv1d_umma_supported(C.byref(d)):
