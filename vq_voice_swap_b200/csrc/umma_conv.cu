@@ -58,6 +58,8 @@ struct Geo {
   int tma;                  // 1: raw activations arrive by cp.async.bulk.tensor into the staging ring
   int main_box_w, main_boxes, main_origin_mul, main_origin_off;  // box x0 = t0*mul/2 + off (mul: 1=up2, 2=none, 4=down2)
   int skip_box_w, skip_origin_mul;
+  // persistent scheduling: tiles ordered (sample, n tile, t tile); each CTA owns a contiguous range
+  int tiles_t, tiles_total, tiles_per_cta;
 };
 
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
@@ -104,7 +106,8 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->stage_bytes = g->kbs * per_kb;
   g->raw_stage_bytes = g->kbs * g->raw_kb_bytes;
   g->a_stage_bytes = g->kbs * g->a_kb_bytes;
-  g->param_bytes = ((2 * c_in * 4 + g->n_tile * 4) + 127) / 128 * 128;
+  g->param_bytes = ((2 * 256 * 4 + 2 * c_in * 4 + g->n_tile * 4) + 127) / 128 * 128;
+  g->tiles_t = g->tiles_total = g->tiles_per_cta = 0;  // filled at launch
   const int fixed = SMEM_HEADER + g->param_bytes;
   int stages = (112 * 1024 - fixed) / g->stage_bytes;  // two CTAs per SM when it fits
   if (stages < 2) stages = (225 * 1024 - fixed) / g->stage_bytes;
@@ -351,24 +354,32 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // bars[0..3] full_ld (TMA: raw activations + weights), [4..7] full_a (operand tile written),
-  // [8..11] empty (MMAs of the stage retired), [12] acc_full
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 13 * 8);
+  // [8..11] empty (MMAs of the stage retired), [12] acc_full, [13] acc_empty (epilogue drained TMEM)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 14 * 8);
+  float* s_stat = reinterpret_cast<float*>(smem + SMEM_HEADER);  // [2][n_tile] per-tile (sum, sumsq) combine
   const int c_in = d.c_a + d.c_b;
-  float2* s_ss = reinterpret_cast<float2*>(smem + SMEM_HEADER);
+  float2* s_ss = reinterpret_cast<float2*>(smem + SMEM_HEADER + 2 * 256 * 4);
   float* s_bias = reinterpret_cast<float*>(s_ss + c_in);
   uint8_t* stage0 = smem + SMEM_HEADER + g.param_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.z, nt = blockIdx.y, t0 = blockIdx.x * TILE_M;
+  const int tile_lo = blockIdx.x * g.tiles_per_cta;
+  const int tile_hi = min(tile_lo + g.tiles_per_cta, g.tiles_total);
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t acc_full = bar0 + 8u * 12;
+  const uint32_t acc_empty = bar0 + 8u * 13;
+#define TILE_COORDS(tile)                                   \
+  const int tx_ = (tile) % g.tiles_t;                       \
+  const int nt = ((tile) / g.tiles_t) % g.n_tiles;          \
+  const int n = (tile) / (g.tiles_t * g.n_tiles);           \
+  const int t0 = tx_ * TILE_M;
 #define FULL_LD(s) (bar0 + 8u * (s))
 #define FULL_A(s) (bar0 + 8u * (4 + (s)))
 #define EMPTY(s) (bar0 + 8u * (8 + (s)))
@@ -380,6 +391,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       mbar_init(EMPTY(s), 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, PRODUCER_THREADS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_holder), g.tmem_cols);
@@ -391,30 +403,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       if (d.s_b) tma_prefetch_desc(&tm_sb);
     }
   }
-  if (d.act) {
-    for (int i = threadIdx.x; i < c_in; i += THREADS)
-      s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
-  }
-  for (int i = threadIdx.x; i < g.n_tile; i += THREADS) {
-    const int co = nt * g.n_tile + i;
-    float b = d.bias ? d.bias[co] : 0.f;
-    if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
-    s_bias[i] = b;
-  }
+  for (int i = threadIdx.x; i < 2 * 256; i += THREADS) s_stat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   const int total_stages = g.main_stages + g.skip_stages;
+  int it = 0;  // pipeline stage counter, runs on across tiles (identical sequence in every role)
 
   if (warp < PRODUCER_WARPS) {
     // =========================== operand producers ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
-    for (int st = 0; st < total_stages; ++st) {
-      const int s = st % g.stages;
-      const uint32_t ph = (st / g.stages) & 1;
+    int staged_n = -1, staged_nt = -1;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    TILE_COORDS(tile)
+    if (n != staged_n || nt != staged_nt) {  // per-sample GroupNorm/FiLM affine and the bias slice of this N tile
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS));
+      if (d.act && n != staged_n)
+        for (int i = threadIdx.x; i < c_in; i += PRODUCER_THREADS)
+          s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
+      for (int i = threadIdx.x; i < g.n_tile; i += PRODUCER_THREADS) {
+        const int co = nt * g.n_tile + i;
+        float b = d.bias ? d.bias[co] : 0.f;
+        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
+        s_bias[i] = b;
+      }
+      staged_n = n;
+      staged_nt = nt;
+      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS));
+    }
+    for (int st = 0; st < total_stages; ++st, ++it) {
+      const int s = it % g.stages;
+      const uint32_t ph = (it / g.stages) & 1;
       mbar_wait(EMPTY(s), ph ^ 1);
       uint8_t* stage = stage0 + (size_t)s * g.stage_bytes;
       uint8_t* a_stage = stage + g.raw_stage_bytes;
@@ -542,7 +564,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
 
     // =========================== epilogue ===========================
-    mbar_wait(acc_full, 0);
+    const uint32_t tile_par = (uint32_t)(tile - tile_lo) & 1;
+    mbar_wait(acc_full, tile_par);
     tc_fence_after();
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
     const int half = warp >> 2;    // the two warps of a quarter split the columns
@@ -550,24 +573,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const int t = t0 + row;
     const bool t_ok = t < d.t_out;
     const int n_chunks32 = g.n_tile / 32;
+    bool released = false;  // this thread's acc_empty arrival (exactly one per tile)
     for (int ch = half; ch < n_chunks32; ch += 2) {
       if (d.reserved_ & 16) break;
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, v);
       const int co0 = nt * g.n_tile + ch * 32;
+      if (ch + 2 >= n_chunks32 && !((g.n_tile & 31) && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        released = true;
+      }
       float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
+      if (d.skip_mode == VQVS_SKIP_IDENTITY && t_ok) {
+        // all 32 skip loads first (they cannot be hoisted over the stores below by the compiler)
+        float sk[32];
+        const bool from_a = co0 < d.s_a;  // chunks never straddle the concat boundary (multiples of 32 in practice)
+        const float* sp = from_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
+        if (d.skip_resize == VQVS_RESIZE_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + t);
+        } else if (d.skip_resize == VQVS_RESIZE_UP2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + (t >> 1));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)j * d.t_skip + 2 * t));
+            sk[j] = 0.5f * (p.x + p.y);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += sk[j];
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float o = v[j] + s_bias[ch * 32 + j];
         if (t_ok) {
-          if (d.skip_mode == VQVS_SKIP_IDENTITY) {
-            const int co = co0 + j;
-            const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
-                                         : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
-            if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
-            else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
-            else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
-          }
           if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
         } else {
           o = 0.f;
@@ -578,17 +620,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         float sq[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        const float s1 = column_sums32(v, lane);
         const float s2 = column_sums32(sq, lane);
-        double* st = d.stats_out + ((size_t)n * d.c_out + co0 + lane) * 2;
-        atomicAdd(st, (double)s1);
-        atomicAdd(st + 1, (double)s2);
+        const float s1 = column_sums32(v, lane);
+        atomicAdd(s_stat + ch * 32 + lane, s1);        // combine the four row quarters in shared memory
+        atomicAdd(s_stat + 256 + ch * 32 + lane, s2);
       }
     }
     if ((g.n_tile & 31) && half == 0) {  // trailing 16 columns (tiny configurations only)
       float v[16];
       const int cbase = n_chunks32 * 32;
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + cbase, v);
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      released = true;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int co = nt * g.n_tile + cbase + j;
@@ -608,21 +652,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (d.stats_out) {
           const float s1 = warp_sum(o), s2 = warp_sum(o * o);
           if (lane == 0) {
-            double* st = d.stats_out + ((size_t)n * d.c_out + co) * 2;
-            atomicAdd(st, (double)s1);
-            atomicAdd(st + 1, (double)s2);
+            atomicAdd(s_stat + cbase + j, s1);
+            atomicAdd(s_stat + 256 + cbase + j, s2);
           }
         }
       }
     }
+    if (!released) {  // warps without any chunk of this tile still owe their arrival
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+    if (d.stats_out && !(d.reserved_ & 1)) {
+      // one fp64 atomic per (channel, statistic) and tile instead of one per row quarter
+      asm volatile("bar.sync 2, %0;" ::"n"(PRODUCER_THREADS));
+      for (int i = threadIdx.x; i < 2 * g.n_tile; i += PRODUCER_THREADS) {
+        const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
+        const float val = s_stat[which * 256 + c];
+        s_stat[which * 256 + c] = 0.f;
+        atomicAdd(d.stats_out + ((size_t)n * d.c_out + nt * g.n_tile + c) * 2 + which, (double)val);
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(PRODUCER_THREADS));
+    }
+    }  // tile loop
     tc_fence_before();
   } else if (warp == TMA_WARP) {
     // =========================== TMA issuer: raw activation boxes + weight image ===========================
     if (lane == 0) {
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      TILE_COORDS(tile)
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
-      for (int st = 0; st < total_stages; ++st) {
-        const int s = st % g.stages;
-        const uint32_t ph = (st / g.stages) & 1;
+      for (int st = 0; st < total_stages; ++st, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(EMPTY(s), ph ^ 1);
         const bool is_skip = st >= g.main_stages;
         const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
@@ -650,16 +711,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
         tma_bulk_g2s(smem_u32(stage + g.raw_stage_bytes + g.a_stage_bytes), src, nk * unit, FULL_LD(s));
       }
+      }  // tile loop
     }
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(g.n_tile);
       const uint32_t a_lbo = g.rows * 16, b_lbo = g.n_tile * 16;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
       uint32_t acc = 0;
-      for (int st = 0; st < total_stages; ++st) {
-        const int s = st % g.stages;
-        const uint32_t ph = (st / g.stages) & 1;
+      mbar_wait(acc_empty, ((uint32_t)(tile - tile_lo) & 1) ^ 1);  // epilogue of the previous tile has drained TMEM
+      tc_fence_after();
+      for (int st = 0; st < total_stages; ++st, ++it) {
+        const int s = it % g.stages;
+        const uint32_t ph = (it / g.stages) & 1;
         mbar_wait(FULL_LD(s), ph);
         mbar_wait(FULL_A(s), ph);
         tc_fence_after();
@@ -691,6 +756,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         mma_commit(EMPTY(s));
       }
       mma_commit(acc_full);
+      }  // tile loop
     }
   }
   __syncthreads();
@@ -698,6 +764,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
+#undef TILE_COORDS
 #undef FULL_LD
 #undef FULL_A
 #undef EMPTY
@@ -959,7 +1026,18 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
       if (d->s_b && (rc = encode_map(&maps[3], d->sb, d->batch * d->s_b, d->t_skip, g.skip_box_w))) return rc;
     }
   }
-  dim3 grid(ceil_div(d->t_out, umma::TILE_M), g.n_tiles, d->batch);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int cc = 0;
+    if (vqvs_device_info(&cc, &sm_count) != VQVS_OK) return VQVS_ECUDA;
+  }
+  g.tiles_t = ceil_div(d->t_out, umma::TILE_M);
+  g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
+  const int ctas_per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;
+  int grid = sm_count * ctas_per_sm;
+  if (grid > g.tiles_total) grid = g.tiles_total;
+  g.tiles_per_cta = ceil_div(g.tiles_total, grid);
+  grid = ceil_div(g.tiles_total, g.tiles_per_cta);
   umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
