@@ -247,7 +247,7 @@ def test_fused_sampler_matches_unfused(monkeypatch, backend):
         fused = m.diffusion.ddpm_sample(x_T, m.predictor, 3, constrain=constrain)
         _Noise("fuse", monkeypatch)
         unfused = m.diffusion.ddpm_sample(x_T, lambda x, t: m.predictor(x, t), 3, constrain=constrain)
-        assert rel_l2(fused.cpu(), unfused.cpu()) <= 1e-6
+        assert rel_l2(fused.cpu(), unfused.cpu()) <= 1e-4  # statistics use atomics: summation order varies run to run
 
 
 def test_cpu_tensors_fail_loudly():
