@@ -14,9 +14,10 @@
 // * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), three MMAs per
 //   K block: hi*hi + lo*hi + hi*lo  ("bf16x3": ~2^-16 relative operand error, measured 1.5e-5 on a
 //   whole UNet forward vs 9.7e-4 for single TF32 -- tools/precision_study.py).
-// * The producer warps then read the accumulator back with tcgen05.ld, add bias / identity skip,
-//   store coalesced along time, and reduce per-channel (sum, sumsq) for the next GroupNorm with a
-//   transposing shuffle butterfly + fp64 atomics.
+// * Four epilogue warps read the (double-buffered) accumulator back with tcgen05.ld, add bias /
+//   identity skip, store coalesced along time, and reduce per-channel (sum, sumsq) for the next
+//   GroupNorm with a transposing shuffle butterfly, a shared-memory combine and fp64 atomics --
+//   while the transform/MMA warps already work on the CTA's next tile (persistent CTAs, one per SM).
 // The optional 1x1 skip conv (reference models/unet.py:265-271) is extra K blocks over the raw input.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,30 +30,31 @@ namespace umma {
 
 constexpr int TILE_M = 128;
 constexpr int KBLK = 16;  // channels per MMA K block (kind::f16: K = 16)
-constexpr int PRODUCER_WARPS = 8;
-constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
-constexpr int TMA_WARP = PRODUCER_WARPS;
-constexpr int MMA_WARP = PRODUCER_WARPS + 1;
-constexpr int THREADS = (PRODUCER_WARPS + 2) * 32;
-constexpr int MAX_STAGES = 4;
-constexpr int SMEM_HEADER = 128;  // mbarriers + TMEM base holder
+// warp roles of the persistent CTA (one CTA per SM)
+constexpr int XFORM_WARPS = 9;    // 8 warps transform the 128 main rows x 2 chunks, the 9th the halo rows
+constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
+constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
+constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
+constexpr int EPI_WARP0 = 12;     // warps 12..15 <-> TMEM lane quarters 0..3
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int SMEM_HEADER = 384;  // 33 mbarriers + TMEM base holder
 
 // Host-computed geometry shared by the packer and the kernel.
 struct Geo {
   int n_tiles, n_tile;      // output-channel tiling (n_tile <= 256, multiple of 16)
-  int nkb_main, nkb_skip;   // K blocks of the main taps / of the 1x1 skip
-  int kbs;                  // K blocks per pipeline stage
-  int pad, rows;            // halo and A rows (= 128 + 2*pad)
-  int stages, main_stages, skip_stages;
-  int tmem_cols;
-  int a_kb_bytes;           // A bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
-  int b_unit_main;          // W bytes per main K block: ksize taps x hi/lo x 2 chunks x n_tile rows x 16 B
-  int b_unit_skip;          // W bytes per skip K block
-  int raw_kb_bytes;         // raw fp32 staging per K block (TMA mode): 16 channels x widest box
-  int stage_bytes;          // kbs * (raw_kb_bytes + a_kb_bytes + b_unit_main)
-  int raw_stage_bytes, a_stage_bytes;
-  int param_bytes;          // (scale, shift) pairs + bias staging
-  long long per_tile_bytes; // packed image bytes per N tile
+  int nkb_main, nkb_skip;   // K blocks (16 channels) of the main taps / of the 1x1 skip
+  int pad, rows;            // halo and operand rows (= 128 + 2*pad)
+  int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
+  int a_kb_bytes;           // operand bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
+  int b_unit_main;          // weight bytes per main K block: ksize taps x hi/lo x 2 chunks x n_tile rows x 16 B
+  int b_unit_skip;          // weight bytes per skip K block
+  long long per_tile_bytes; // packed weight image bytes per N tile
+  // shared-memory plan (byte offsets from the dynamic smem base)
+  int off_stat, off_ss, off_bias, off_w, off_raw, off_ab;
+  int raw_slot_bytes, raw_slots;  // fp32 staging ring filled by TMA (0 slots in direct mode)
+  int ab_slot_bytes, ab_slots;    // operand ring: A tile (+ streamed weights of the K block)
+  int w_resident;                 // 1: the whole weight image of the N tile stays in smem for all tiles of the CTA
   int smem_bytes;
   // TMA activation boxes, in SOURCE coordinates relative to the tile origin
   int tma;                  // 1: raw activations arrive by cp.async.bulk.tensor into the staging ring
@@ -63,6 +65,7 @@ struct Geo {
 };
 
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
@@ -77,8 +80,13 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->a_kb_bytes = g->rows * 64;
   g->b_unit_main = ksize * g->n_tile * 64;
   g->b_unit_skip = g->n_tile * 64;
+  g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
+  int cols = 32;
+  while (cols < g->n_tile) cols *= 2;
+  g->acc_cols = cols;
+  g->tmem_cols = 2 * cols;
   g->tma = tma ? 1 : 0;
-  g->raw_kb_bytes = 0;
+  g->raw_slot_bytes = 0;
   g->main_box_w = g->main_boxes = g->main_origin_mul = g->main_origin_off = g->skip_box_w = g->skip_origin_mul = 0;
   if (tma) {
     const int off = round_up4(g->pad);
@@ -98,28 +106,36 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
       if (g->skip_box_w > widest) widest = g->skip_box_w;
     }
     if (g->main_box_w > 256 || g->skip_box_w > 256) return false;
-    g->raw_kb_bytes = KBLK * widest * 4;
+    g->raw_slot_bytes = KBLK * widest * 4;
   }
-  const int per_kb = g->raw_kb_bytes + g->a_kb_bytes + g->b_unit_main;
-  int kbs = (40 * 1024) / per_kb;
-  g->kbs = kbs < 1 ? 1 : (kbs > 4 ? 4 : kbs);
-  g->stage_bytes = g->kbs * per_kb;
-  g->raw_stage_bytes = g->kbs * g->raw_kb_bytes;
-  g->a_stage_bytes = g->kbs * g->a_kb_bytes;
-  g->param_bytes = ((2 * 256 * 4 + 2 * c_in * 4 + g->n_tile * 4) + 127) / 128 * 128;
+  // ---- shared-memory plan: one persistent CTA per SM -----------------------------------------
+  const int budget = 225 * 1024;
+  int off = SMEM_HEADER;
+  g->off_stat = off; off += 2 * 256 * 4;
+  g->off_ss = off;   off += c_in * 8;
+  g->off_bias = off; off += g->n_tile * 4;
+  off = align_up(off, 128);
+  g->off_w = off;
+  const long long w_img = g->per_tile_bytes;
+  g->w_resident = (g->n_tiles == 1 && w_img <= 100 * 1024) ? 1 : 0;
+  if (g->w_resident) off += (int)w_img;
+  g->off_raw = off;
+  const int b_slot = g->w_resident ? 0 : g->b_unit_main;
+  g->ab_slot_bytes = g->a_kb_bytes + b_slot;
+  int left = budget - off;
+  // operand ring first (2..4 slots), the rest of the budget is raw prefetch depth (<= 8 slots)
+  int ab = 4;
+  while (ab > 2 && left - ab * g->ab_slot_bytes < (tma ? 3 * g->raw_slot_bytes : 0)) --ab;
+  if (left < ab * g->ab_slot_bytes + (tma ? 2 * g->raw_slot_bytes : 0)) return false;
+  g->ab_slots = ab;
+  left -= ab * g->ab_slot_bytes;
+  int raw = tma ? left / g->raw_slot_bytes : 0;
+  g->raw_slots = raw > 8 ? 8 : raw;
+  off += g->raw_slots * g->raw_slot_bytes;
+  g->off_ab = off;
+  off += g->ab_slots * g->ab_slot_bytes;
+  g->smem_bytes = off;
   g->tiles_t = g->tiles_total = g->tiles_per_cta = 0;  // filled at launch
-  const int fixed = SMEM_HEADER + g->param_bytes;
-  int stages = (112 * 1024 - fixed) / g->stage_bytes;  // two CTAs per SM when it fits
-  if (stages < 2) stages = (225 * 1024 - fixed) / g->stage_bytes;
-  if (stages < 2) return false;
-  g->stages = stages > MAX_STAGES ? MAX_STAGES : stages;
-  g->main_stages = (g->nkb_main + g->kbs - 1) / g->kbs;
-  g->skip_stages = (g->nkb_skip + g->kbs - 1) / g->kbs;
-  int cols = 32;
-  while (cols < g->n_tile) cols *= 2;
-  g->tmem_cols = cols;
-  g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
-  g->smem_bytes = fixed + g->stages * g->stage_bytes;
   return true;
 }
 
@@ -354,48 +370,131 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
+// Transform one item: 8 channels (one 16-B operand chunk) at conv position(s) -> bf16 hi/lo rows.
+struct StageView {
+  const float* raw;   // raw slot (TMA mode)
+  uint8_t* a;         // operand slot
+  int rows;           // operand rows of this conv (row pitch of the hi/lo blocks)
+  int box_w, boxes, x0, tcs, n_rows, t_src, t_conv, resize;
+  bool act;
+  const float4* ss;   // (scale, shift) pairs of the 16 channels of this K block
+};
+
+__device__ __forceinline__ void transform_rowwise(const StageView& v, int chunk, int row) {
+  const int tc = v.tcs + row;
+  float x[8];
+  if (tc >= 0 && tc < v.t_conv) {
+    if (v.resize != VQVS_RESIZE_DOWN2) {
+      const float* raw = v.raw + (chunk * 8) * v.box_w + (tc - v.x0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
+      if (v.act) affine_gelu8(x, v.ss + chunk * 4);
+    } else {
+      int col = 2 * tc - v.x0;
+      const float* raw = v.raw;
+      if (v.boxes == 2 && col >= v.box_w) {
+        col -= v.box_w;
+        raw += KBLK * v.box_w;
+      }
+      raw += (chunk * 8) * v.box_w + col;
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 p = *reinterpret_cast<const float2*>(raw + e * v.box_w);
+        x[e] = p.x;
+        w[e] = p.y;
+      }
+      if (v.act) {
+        affine_gelu8(x, v.ss + chunk * 4);
+        affine_gelu8(w, v.ss + chunk * 4);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = 0.5f * (x[e] + w[e]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+  }
+  uint8_t* a_hi = v.a + chunk * (v.rows * 16);
+  store_rows(x, a_hi, a_hi + v.rows * 32, row);
+}
+
+// nearest x2: one item = one SOURCE position -> two operand rows (GELU evaluated once)
+__device__ __forceinline__ void transform_up2(const StageView& v, int chunk, int ts) {
+  float x[8];
+  if (ts >= 0 && ts < v.t_src) {
+    const float* raw = v.raw + (chunk * 8) * v.box_w + (ts - v.x0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
+    if (v.act) affine_gelu8(x, v.ss + chunk * 4);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+  }
+  uint4 hi, lo;
+  split8(x, &hi, &lo);
+  uint8_t* a_hi = v.a + chunk * (v.rows * 16);
+  uint8_t* a_lo = a_hi + v.rows * 32;
+  const int r0 = 2 * ts - v.tcs;
+  if (r0 >= 0 && r0 < v.n_rows) {
+    *reinterpret_cast<uint4*>(a_hi + r0 * 16) = hi;
+    *reinterpret_cast<uint4*>(a_lo + r0 * 16) = lo;
+  }
+  if (r0 + 1 >= 0 && r0 + 1 < v.n_rows) {
+    *reinterpret_cast<uint4*>(a_hi + (r0 + 1) * 16) = hi;
+    *reinterpret_cast<uint4*>(a_lo + (r0 + 1) * 16) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // bars[0..3] full_ld (TMA: raw activations + weights), [4..7] full_a (operand tile written),
-  // [8..11] empty (MMAs of the stage retired), [12] acc_full, [13] acc_empty (epilogue drained TMEM)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 14 * 8);
-  float* s_stat = reinterpret_cast<float*>(smem + SMEM_HEADER);  // [2][n_tile] per-tile (sum, sumsq) combine
+  // mbarriers: raw_full[8] raw_empty[8] b_full[4] a_full[4] ab_empty[4] acc_full[2] acc_empty[2] w_full
+  const uint32_t bar0 = smem_u32(smem);
+#define RAW_FULL(i) (bar0 + 8u * (i))
+#define RAW_EMPTY(i) (bar0 + 8u * (8 + (i)))
+#define B_FULL(i) (bar0 + 8u * (16 + (i)))
+#define A_FULL(i) (bar0 + 8u * (20 + (i)))
+#define AB_EMPTY(i) (bar0 + 8u * (24 + (i)))
+#define ACC_FULL(i) (bar0 + 8u * (28 + (i)))
+#define ACC_EMPTY(i) (bar0 + 8u * (30 + (i)))
+#define W_FULL (bar0 + 8u * 32)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 33 * 8);
+  float* s_stat = reinterpret_cast<float*>(smem + g.off_stat);  // [2][256] per-tile (sum, sumsq) combine
+  float2* s_ss = reinterpret_cast<float2*>(smem + g.off_ss);    // (scale, shift) of the current sample
+  float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
   const int c_in = d.c_a + d.c_b;
-  float2* s_ss = reinterpret_cast<float2*>(smem + SMEM_HEADER + 2 * 256 * 4);
-  float* s_bias = reinterpret_cast<float*>(s_ss + c_in);
-  uint8_t* stage0 = smem + SMEM_HEADER + g.param_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_lo = blockIdx.x * g.tiles_per_cta;
   const int tile_hi = min(tile_lo + g.tiles_per_cta, g.tiles_total);
-  const uint32_t bar0 = smem_u32(bars);
-  const uint32_t acc_full = bar0 + 8u * 12;
-  const uint32_t acc_empty = bar0 + 8u * 13;
-#define TILE_COORDS(tile)                                   \
-  const int tx_ = (tile) % g.tiles_t;                       \
-  const int nt = ((tile) / g.tiles_t) % g.n_tiles;          \
-  const int n = (tile) / (g.tiles_t * g.n_tiles);           \
+#define TILE_COORDS(tile)                          \
+  const int tx_ = (tile) % g.tiles_t;              \
+  const int nt = ((tile) / g.tiles_t) % g.n_tiles; \
+  const int n = (tile) / (g.tiles_t * g.n_tiles);  \
   const int t0 = tx_ * TILE_M;
-#define FULL_LD(s) (bar0 + 8u * (s))
-#define FULL_A(s) (bar0 + 8u * (4 + (s)))
-#define EMPTY(s) (bar0 + 8u * (8 + (s)))
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(FULL_LD(s), 1);
-      mbar_init(FULL_A(s), PRODUCER_THREADS);
-      mbar_init(EMPTY(s), 1);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(RAW_FULL(i), 1);
+      mbar_init(RAW_EMPTY(i), XFORM_WARPS);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, PRODUCER_THREADS);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(B_FULL(i), 1);
+      mbar_init(A_FULL(i), XFORM_WARPS);
+      mbar_init(AB_EMPTY(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ACC_FULL(i), 1);
+      mbar_init(ACC_EMPTY(i), EPI_WARPS * 32);
+    }
+    mbar_init(W_FULL, 1);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_holder), g.tmem_cols);
-  if (warp == TMA_WARP && lane == 0 && g.tma) {
+  if (warp == TMA_RAW_WARP && lane == 0 && g.tma) {
     tma_prefetch_desc(&tm_xa);
     if (d.c_b) tma_prefetch_desc(&tm_xb);
     if (g.nkb_skip) {
@@ -408,356 +507,311 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const int total_k = g.nkb_main + g.nkb_skip;  // pipeline steps (K blocks) per tile
 
-  const int total_stages = g.main_stages + g.skip_stages;
-  int it = 0;  // pipeline stage counter, runs on across tiles (identical sequence in every role)
-
-  if (warp < PRODUCER_WARPS) {
-    // =========================== operand producers ===========================
+  if (warp < XFORM_WARPS) {
+    // =========================== operand producers (transform warps) ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
-    int staged_n = -1, staged_nt = -1;
+    int it = 0, staged_n = -1;
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
-    TILE_COORDS(tile)
-    if (n != staged_n || nt != staged_nt) {  // per-sample GroupNorm/FiLM affine and the bias slice of this N tile
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS));
-      if (d.act && n != staged_n)
-        for (int i = threadIdx.x; i < c_in; i += PRODUCER_THREADS)
+      TILE_COORDS(tile)
+      (void)nt;
+      if (d.act && n != staged_n) {  // per-sample GroupNorm/FiLM affine
+        asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
+        for (int i = threadIdx.x; i < c_in; i += XFORM_WARPS * 32)
           s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
-      for (int i = threadIdx.x; i < g.n_tile; i += PRODUCER_THREADS) {
-        const int co = nt * g.n_tile + i;
-        float b = d.bias ? d.bias[co] : 0.f;
-        if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
-        s_bias[i] = b;
+        staged_n = n;
+        asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
       }
-      staged_n = n;
-      staged_nt = nt;
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCER_THREADS));
-    }
-    for (int st = 0; st < total_stages; ++st, ++it) {
-      const int s = it % g.stages;
-      const uint32_t ph = (it / g.stages) & 1;
-      mbar_wait(EMPTY(s), ph ^ 1);
-      uint8_t* stage = stage0 + (size_t)s * g.stage_bytes;
-      uint8_t* a_stage = stage + g.raw_stage_bytes;
-      const bool is_skip = st >= g.main_stages;
-      const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
-      const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-      const bool act = !is_skip && d.act;
-      const int pad = is_skip ? 0 : g.pad;
-      const int resize = is_skip ? d.skip_resize : d.resize;
-      const int t_src = is_skip ? d.t_skip : d.t_in;
-      if (!g.tma) {
-        const Src& src = is_skip ? skip_src : main_src;
-        for (int i = threadIdx.x; i < nk * 2 * TILE_M; i += PRODUCER_THREADS) {
-          const int q = i >> 7, m = i & (TILE_M - 1);
-          const int c8 = kb0 * KBLK + q * 8;
-          uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-          produce_direct(src, n, c8, t0 + m, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, pad + m);
+      for (int st = 0; st < total_k; ++st, ++it) {
+        const int s = it % g.ab_slots;
+        mbar_wait(AB_EMPTY(s), ((it / g.ab_slots) & 1) ^ 1);
+        const int r = g.tma ? it % g.raw_slots : 0;
+        const bool is_skip = st >= g.nkb_main;
+        const int kb = is_skip ? st - g.nkb_main : st;
+        const int pad = is_skip ? 0 : g.pad;
+        uint8_t* a_slot = smem + g.off_ab + (size_t)s * g.ab_slot_bytes;
+        if (g.tma) {
+          mbar_wait(RAW_FULL(r), (it / g.raw_slots) & 1);
+          StageView v;
+          v.raw = reinterpret_cast<const float*>(smem + g.off_raw + (size_t)r * g.raw_slot_bytes);
+          v.a = a_slot;
+          v.rows = g.rows;
+          v.box_w = is_skip ? g.skip_box_w : g.main_box_w;
+          v.boxes = is_skip ? 1 : g.main_boxes;
+          v.x0 = (t0 * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2 + (is_skip ? 0 : g.main_origin_off);
+          v.tcs = t0 - pad;
+          v.n_rows = TILE_M + 2 * pad;
+          v.t_src = is_skip ? d.t_skip : d.t_in;
+          v.t_conv = d.t_out;
+          v.resize = is_skip ? d.skip_resize : d.resize;
+          v.act = !is_skip && d.act && !(d.reserved_ & 8);
+          v.ss = reinterpret_cast<const float4*>(s_ss + kb * KBLK);
+          if (v.resize == VQVS_RESIZE_UP2) {
+            const int first = v.tcs >> 1;
+            const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
+            for (int i = threadIdx.x; i < 2 * nsrc; i += XFORM_WARPS * 32) {
+              const int chunk = i >= nsrc, j = chunk ? i - nsrc : i;
+              transform_up2(v, chunk, first + j);
+            }
+          } else {
+            // warps 0..7: the 128 main rows of both chunks; last warp: the 2*pad halo rows
+            if (warp < XFORM_WARPS - 1) {
+              transform_rowwise(v, threadIdx.x >> 7, threadIdx.x & (TILE_M - 1));
+            } else {
+              const int n_extra = v.n_rows - TILE_M;
+              for (int i = lane; i < 2 * n_extra; i += 32) {
+                const int chunk = i >= n_extra;
+                transform_rowwise(v, chunk, TILE_M + (chunk ? i - n_extra : i));
+              }
+            }
+          }
+        } else {
+          const Src& src = is_skip ? skip_src : main_src;
+          const bool act = !is_skip && d.act;
+          const int n_rows = TILE_M + 2 * pad;
+          for (int i = threadIdx.x; i < 2 * n_rows; i += XFORM_WARPS * 32) {
+            const int chunk = i >= n_rows, row = chunk ? i - n_rows : i;
+            const int c8 = kb * KBLK + chunk * 8;
+            uint8_t* a_hi = a_slot + chunk * (g.rows * 16);
+            produce_direct(src, n, c8, t0 - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
+          }
         }
-        const int n_halo = nk * 2 * 2 * pad;
-        for (int i = threadIdx.x; i < n_halo; i += PRODUCER_THREADS) {
-          const int q = i / (2 * pad), e = i - q * (2 * pad);
-          const int row = e < pad ? e : TILE_M + e;
-          const int c8 = kb0 * KBLK + q * 8;
-          uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-          produce_direct(src, n, c8, t0 - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(A_FULL(s));
+          if (g.tma) mbar_arrive(RAW_EMPTY(r));
+        }
+      }
+    }
+  } else if (warp == TMA_RAW_WARP) {
+    // =========================== TMA: raw activation boxes ===========================
+    if (lane == 0 && g.tma) {
+      int it = 0;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        TILE_COORDS(tile)
+        (void)nt;
+        for (int st = 0; st < total_k; ++st, ++it) {
+          const int r = it % g.raw_slots;
+          mbar_wait(RAW_EMPTY(r), ((it / g.raw_slots) & 1) ^ 1);
+          const bool is_skip = st >= g.nkb_main;
+          const int kb = is_skip ? st - g.nkb_main : st;
+          const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
+          const int boxes = is_skip ? 1 : g.main_boxes;
+          const int x0 = (t0 * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2 + (is_skip ? 0 : g.main_origin_off);
+          const int ca = is_skip ? d.s_a : d.c_a, cb = is_skip ? d.s_b : d.c_b;
+          const int c16 = kb * KBLK;
+          const CUtensorMap* map = c16 < ca ? (is_skip ? &tm_sa : &tm_xa) : (is_skip ? &tm_sb : &tm_xb);
+          const int rowc = c16 < ca ? n * ca + c16 : n * cb + (c16 - ca);
+          const uint32_t dst = smem_u32(smem + g.off_raw + (size_t)r * g.raw_slot_bytes);
+          mbar_expect_tx(RAW_FULL(r), boxes * KBLK * box_w * 4);
+          for (int b = 0; b < boxes; ++b) tma_box_2d(dst + b * (KBLK * box_w * 4), map, x0 + b * box_w, rowc, RAW_FULL(r));
+        }
+      }
+    }
+  } else if (warp == TMA_W_WARP) {
+    // =========================== TMA: weight image ===========================
+    if (lane == 0) {
+      if (g.w_resident) {  // loaded once, reused by every tile of this CTA
+        const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed);
+        const uint32_t total = (uint32_t)g.per_tile_bytes;
+        mbar_expect_tx(W_FULL, total);
+        for (uint32_t o = 0; o < total; o += 32768) {
+          const uint32_t nbytes = total - o < 32768 ? total - o : 32768;
+          tma_bulk_g2s(smem_u32(smem + g.off_w + o), wimg + o, nbytes, W_FULL);
         }
       } else {
-        mbar_wait(FULL_LD(s), ph);  // raw fp32 boxes have landed
-        const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
-        const int mul = is_skip ? g.skip_origin_mul : g.main_origin_mul;
-        const int x0 = (t0 * mul) / 2 + (is_skip ? 0 : g.main_origin_off);  // source position of raw column 0
-        const int tcs = t0 - pad;                                           // conv position of row 0
-        const int rows = TILE_M + 2 * pad;
-        if (resize == VQVS_RESIZE_UP2) {
-          // one item = 8 channels x one SOURCE position -> two output rows (GELU evaluated once)
-          const int first = tcs >> 1;
-          const int nsrc = ((tcs + rows - 1) >> 1) - first + 1;
-          for (int i = threadIdx.x; i < nk * 2 * nsrc; i += PRODUCER_THREADS) {
-            const int q = i / nsrc, j = i - q * nsrc;
-            const int ts = first + j;
-            const float* raw = reinterpret_cast<const float*>(stage + (q >> 1) * g.raw_kb_bytes) + ((q & 1) * 8) * box_w + (ts - x0);
-            float v[8];
-            if (ts >= 0 && ts < t_src) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = raw[e * box_w];
-              if (act) affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            }
-            uint4 hi, lo;
-            split8(v, &hi, &lo);
-            uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-            uint8_t* a_lo = a_hi + g.rows * 32;
-            const int r0 = 2 * ts - tcs;
-            if (r0 >= 0) {
-              *reinterpret_cast<uint4*>(a_hi + r0 * 16) = hi;
-              *reinterpret_cast<uint4*>(a_lo + r0 * 16) = lo;
-            }
-            if (r0 + 1 < rows) {
-              *reinterpret_cast<uint4*>(a_hi + (r0 + 1) * 16) = hi;
-              *reinterpret_cast<uint4*>(a_lo + (r0 + 1) * 16) = lo;
-            }
-          }
-        } else {
-          const bool down = resize == VQVS_RESIZE_DOWN2;
-          const int boxes = is_skip ? 1 : g.main_boxes;
-          // rows [0, rows) of every 8-channel chunk; the few halo rows beyond 128 go to one rotating warp
-          const int per_chunk_main = TILE_M, n_extra = rows - TILE_M;
-          for (int pass = 0; pass < 2; ++pass) {
-            const int count = nk * 2 * (pass == 0 ? per_chunk_main : n_extra);
-            if (pass == 1 && (count == 0 || warp != (st & (PRODUCER_WARPS - 1)))) break;
-            for (int i = (pass == 0 ? (int)threadIdx.x : lane); i < count; i += (pass == 0 ? PRODUCER_THREADS : 32)) {
-              int q, row;
-              if (pass == 0) {
-                q = i >> 7;
-                row = i & (TILE_M - 1);
-              } else {
-                q = i / n_extra;
-                row = TILE_M + (i - q * n_extra);
-              }
-              const int tc = tcs + row;
-              const float* raw_k = reinterpret_cast<const float*>(stage + (q >> 1) * g.raw_kb_bytes);
-              float v[8];
-              if (tc >= 0 && tc < d.t_out && !(d.reserved_ & 8)) {
-                if (!down) {
-                  const float* raw = raw_k + ((q & 1) * 8) * box_w + (tc - x0);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = raw[e * box_w];
-                  if (act) affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
-                } else {
-                  int col = 2 * tc - x0;
-                  const float* raw = raw_k;
-                  if (boxes == 2 && col >= box_w) {
-                    col -= box_w;
-                    raw += KBLK * box_w;
-                  }
-                  raw += ((q & 1) * 8) * box_w + col;
-                  float w[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float2 p = *reinterpret_cast<const float2*>(raw + e * box_w);
-                    v[e] = p.x;
-                    w[e] = p.y;
-                  }
-                  if (act) {
-                    affine_gelu8(v, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
-                    affine_gelu8(w, reinterpret_cast<const float4*>(s_ss + kb0 * KBLK + q * 8));
-                  }
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = 0.5f * (v[e] + w[e]);
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-              }
-              uint8_t* a_hi = a_stage + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-              store_rows(v, a_hi, a_hi + g.rows * 32, row);
-            }
-          }
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(FULL_A(s));
-    }
-
-    // =========================== epilogue ===========================
-    const uint32_t tile_par = (uint32_t)(tile - tile_lo) & 1;
-    mbar_wait(acc_full, tile_par);
-    tc_fence_after();
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
-    const int half = warp >> 2;    // the two warps of a quarter split the columns
-    const int row = quarter * 32 + lane;
-    const int t = t0 + row;
-    const bool t_ok = t < d.t_out;
-    const int n_chunks32 = g.n_tile / 32;
-    bool released = false;  // this thread's acc_empty arrival (exactly one per tile)
-    for (int ch = half; ch < n_chunks32; ch += 2) {
-      if (d.reserved_ & 16) break;
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, v);
-      const int co0 = nt * g.n_tile + ch * 32;
-      if (ch + 2 >= n_chunks32 && !((g.n_tile & 31) && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
-        tc_fence_before();
-        mbar_arrive(acc_empty);
-        released = true;
-      }
-      float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
-      if (d.skip_mode == VQVS_SKIP_IDENTITY && t_ok) {
-        // all 32 skip loads first (they cannot be hoisted over the stores below by the compiler)
-        float sk[32];
-        const bool from_a = co0 < d.s_a;  // chunks never straddle the concat boundary (multiples of 32 in practice)
-        const float* sp = from_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
-        if (d.skip_resize == VQVS_RESIZE_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + t);
-        } else if (d.skip_resize == VQVS_RESIZE_UP2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + (t >> 1));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)j * d.t_skip + 2 * t));
-            sk[j] = 0.5f * (p.x + p.y);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += sk[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float o = v[j] + s_bias[ch * 32 + j];
-        if (t_ok) {
-          if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
-        } else {
-          o = 0.f;
-        }
-        v[j] = o;
-      }
-      if (d.stats_out && !(d.reserved_ & 1)) {
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        const float s2 = column_sums32(sq, lane);
-        const float s1 = column_sums32(v, lane);
-        atomicAdd(s_stat + ch * 32 + lane, s1);        // combine the four row quarters in shared memory
-        atomicAdd(s_stat + 256 + ch * 32 + lane, s2);
-      }
-    }
-    if ((g.n_tile & 31) && half == 0) {  // trailing 16 columns (tiny configurations only)
-      float v[16];
-      const int cbase = n_chunks32 * 32;
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + cbase, v);
-      tc_fence_before();
-      mbar_arrive(acc_empty);
-      released = true;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int co = nt * g.n_tile + cbase + j;
-        float o = v[j] + s_bias[cbase + j];
-        if (t_ok) {
-          if (d.skip_mode == VQVS_SKIP_IDENTITY) {
-            const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
-                                         : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
-            if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
-            else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
-            else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
-          }
-          d.out[((size_t)n * d.c_out + co) * d.t_out + t] = o;
-        } else {
-          o = 0.f;
-        }
-        if (d.stats_out) {
-          const float s1 = warp_sum(o), s2 = warp_sum(o * o);
-          if (lane == 0) {
-            atomicAdd(s_stat + cbase + j, s1);
-            atomicAdd(s_stat + 256 + cbase + j, s2);
+        int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+          TILE_COORDS(tile)
+          (void)n; (void)t0;
+          const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
+          for (int st = 0; st < total_k; ++st, ++it) {
+            const int s = it % g.ab_slots;
+            mbar_wait(AB_EMPTY(s), ((it / g.ab_slots) & 1) ^ 1);
+            const bool is_skip = st >= g.nkb_main;
+            const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
+            const uint8_t* src = is_skip ? wimg + (size_t)g.nkb_main * g.b_unit_main + (size_t)(st - g.nkb_main) * g.b_unit_skip
+                                         : wimg + (size_t)st * g.b_unit_main;
+            mbar_expect_tx(B_FULL(s), unit);
+            tma_bulk_g2s(smem_u32(smem + g.off_ab + (size_t)s * g.ab_slot_bytes + g.a_kb_bytes), src, unit, B_FULL(s));
           }
         }
       }
     }
-    if (!released) {  // warps without any chunk of this tile still owe their arrival
-      tc_fence_before();
-      mbar_arrive(acc_empty);
-    }
-    if (d.stats_out && !(d.reserved_ & 1)) {
-      // one fp64 atomic per (channel, statistic) and tile instead of one per row quarter
-      asm volatile("bar.sync 2, %0;" ::"n"(PRODUCER_THREADS));
-      for (int i = threadIdx.x; i < 2 * g.n_tile; i += PRODUCER_THREADS) {
-        const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
-        const float val = s_stat[which * 256 + c];
-        s_stat[which * 256 + c] = 0.f;
-        atomicAdd(d.stats_out + ((size_t)n * d.c_out + nt * g.n_tile + c) * 2 + which, (double)val);
-      }
-      asm volatile("bar.sync 2, %0;" ::"n"(PRODUCER_THREADS));
-    }
-    }  // tile loop
-    tc_fence_before();
-  } else if (warp == TMA_WARP) {
-    // =========================== TMA issuer: raw activation boxes + weight image ===========================
-    if (lane == 0) {
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-      TILE_COORDS(tile)
-      const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
-      for (int st = 0; st < total_stages; ++st, ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (it / g.stages) & 1;
-        mbar_wait(EMPTY(s), ph ^ 1);
-        const bool is_skip = st >= g.main_stages;
-        const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
-        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-        const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
-        const uint8_t* src = wimg + (is_skip ? (size_t)g.nkb_main * g.b_unit_main + (size_t)kb0 * g.b_unit_skip
-                                             : (size_t)kb0 * g.b_unit_main);
-        uint8_t* stage = stage0 + (size_t)s * g.stage_bytes;
-        const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
-        const int boxes = is_skip ? 1 : g.main_boxes;
-        uint32_t bytes = nk * unit;
-        if (g.tma) bytes += nk * boxes * KBLK * box_w * 4;
-        mbar_expect_tx(FULL_LD(s), bytes);
-        if (g.tma) {
-          const int mul = is_skip ? g.skip_origin_mul : g.main_origin_mul;
-          const int x0 = (t0 * mul) / 2 + (is_skip ? 0 : g.main_origin_off);
-          const int ca = is_skip ? d.s_a : d.c_a, cb = is_skip ? d.s_b : d.c_b;
-          for (int k = 0; k < nk; ++k) {
-            const int c16 = (kb0 + k) * KBLK;
-            const CUtensorMap* map = c16 < ca ? (is_skip ? &tm_sa : &tm_xa) : (is_skip ? &tm_sb : &tm_xb);
-            const int rowc = c16 < ca ? n * ca + c16 : n * cb + (c16 - ca);
-            for (int b = 0; b < boxes; ++b)
-              tma_box_2d(smem_u32(stage + k * g.raw_kb_bytes + b * (KBLK * box_w * 4)), map, x0 + b * box_w, rowc, FULL_LD(s));
-          }
-        }
-        tma_bulk_g2s(smem_u32(stage + g.raw_stage_bytes + g.a_stage_bytes), src, nk * unit, FULL_LD(s));
-      }
-      }  // tile loop
-    }
-  } else {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(g.n_tile);
       const uint32_t a_lbo = g.rows * 16, b_lbo = g.n_tile * 16;
+      if (g.w_resident) mbar_wait(W_FULL, 0);
+      int it = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
-      uint32_t acc = 0;
-      mbar_wait(acc_empty, ((uint32_t)(tile - tile_lo) & 1) ^ 1);  // epilogue of the previous tile has drained TMEM
-      tc_fence_after();
-      for (int st = 0; st < total_stages; ++st, ++it) {
-        const int s = it % g.stages;
-        const uint32_t ph = (it / g.stages) & 1;
-        mbar_wait(FULL_LD(s), ph);
-        mbar_wait(FULL_A(s), ph);
+        const int k_local = tile - tile_lo, buf = k_local & 1;
+        mbar_wait(ACC_EMPTY(buf), ((k_local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const bool is_skip = st >= g.main_stages;
-        const int kb0 = is_skip ? (st - g.main_stages) * g.kbs : st * g.kbs;
-        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-        const uint32_t a_base = smem_u32(stage0 + (size_t)s * g.stage_bytes + g.raw_stage_bytes);
-        const uint32_t b_base = a_base + g.a_stage_bytes;
-        const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
-        const int taps = is_skip ? 1 : d.ksize;
-        for (int k = 0; k < nk; ++k) {
-          const uint32_t a_hi = a_base + k * g.a_kb_bytes;
+        const uint32_t d_tmem = tmem_base + buf * g.acc_cols;
+        uint32_t acc = 0;
+        for (int st = 0; st < total_k; ++st, ++it) {
+          const int s = it % g.ab_slots;
+          const uint32_t ph = (it / g.ab_slots) & 1;
+          mbar_wait(A_FULL(s), ph);
+          if (!g.w_resident) mbar_wait(B_FULL(s), ph);
+          tc_fence_after();
+          const bool is_skip = st >= g.nkb_main;
+          const uint32_t a_hi = smem_u32(smem + g.off_ab + (size_t)s * g.ab_slot_bytes);
           const uint32_t a_lo = a_hi + g.rows * 32;
+          uint32_t b_unit;
+          if (g.w_resident)
+            b_unit = smem_u32(smem + g.off_w) + (is_skip ? g.nkb_main * g.b_unit_main + (st - g.nkb_main) * g.b_unit_skip : st * g.b_unit_main);
+          else
+            b_unit = a_hi + g.a_kb_bytes;
+          const int taps = is_skip ? 1 : d.ksize;
           for (int tap = 0; tap < taps; ++tap) {
+            if (d.reserved_ & 4) continue;
             const uint32_t shift = is_skip ? 0u : (uint32_t)(tap * d.dilation * 16);
-            const uint32_t b_hi = b_base + k * unit + tap * (g.n_tile * 64);
+            const uint32_t b_hi = b_unit + tap * (g.n_tile * 64);
             const uint32_t b_lo = b_hi + g.n_tile * 32;
             const uint64_t da_hi = make_desc(a_hi + shift, a_lbo, 128);
             const uint64_t da_lo = make_desc(a_lo + shift, a_lbo, 128);
             const uint64_t db_hi = make_desc(b_hi, b_lbo, 128);
             const uint64_t db_lo = make_desc(b_lo, b_lbo, 128);
-            if (d.reserved_ & 4) continue;
-            mma_bf16(tmem_base, da_hi, db_hi, idesc, acc);
+            mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
             acc = 1;
-            mma_bf16(tmem_base, da_lo, db_hi, idesc, 1);
-            mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
+            mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+            mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+          }
+          mma_commit(AB_EMPTY(s));
+        }
+        mma_commit(ACC_FULL(buf));
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
+    const int etid = threadIdx.x - EPI_WARP0 * 32;
+    int staged_nt = -1;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      TILE_COORDS(tile)
+      if (nt != staged_nt) {  // bias slice of this N tile
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
+        for (int i = etid; i < g.n_tile; i += EPI_WARPS * 32) {
+          const int co = nt * g.n_tile + i;
+          float b = d.bias ? d.bias[co] : 0.f;
+          if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
+          s_bias[i] = b;
+        }
+        staged_nt = nt;
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
+      }
+      const int k_local = tile - tile_lo, buf = k_local & 1;
+      mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_base + buf * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
+      const int row = quarter * 32 + lane;
+      const int t = t0 + row;
+      const bool t_ok = t < d.t_out;
+      const int n_chunks32 = g.n_tile / 32;
+      const bool tail16 = (g.n_tile & 31) != 0;
+      for (int ch = 0; ch < n_chunks32; ++ch) {
+        if (d.reserved_ & 16) break;
+        float v[32];
+        tmem_ld32(acc_addr + ch * 32, v);
+        if (ch == n_chunks32 - 1 && !tail16) {  // last TMEM read: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY(buf));
+        }
+        const int co0 = nt * g.n_tile + ch * 32;
+        float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
+        if (d.skip_mode == VQVS_SKIP_IDENTITY && t_ok) {
+          // all 32 skip loads first (they cannot be hoisted over the stores below by the compiler)
+          float sk[32];
+          const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
+                                        : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
+          if (d.skip_resize == VQVS_RESIZE_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + t);
+          } else if (d.skip_resize == VQVS_RESIZE_UP2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + (t >> 1));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)j * d.t_skip + 2 * t));
+              sk[j] = 0.5f * (p.x + p.y);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += sk[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float o = v[j] + s_bias[ch * 32 + j];
+          if (t_ok) {
+            if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
+          } else {
+            o = 0.f;
+          }
+          v[j] = o;
+        }
+        if (d.stats_out && !(d.reserved_ & 1)) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float s2 = column_sums32(sq, lane);
+          const float s1 = column_sums32(v, lane);
+          atomicAdd(s_stat + ch * 32 + lane, s1);  // combine the four row quarters in shared memory
+          atomicAdd(s_stat + 256 + ch * 32 + lane, s2);
+        }
+      }
+      if (tail16 || (d.reserved_ & 16) || n_chunks32 == 0) {
+        float v[16];
+        const int cbase = n_chunks32 * 32;
+        if (tail16) tmem_ld16(acc_addr + cbase, v);
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY(buf));
+        if (tail16 && !(d.reserved_ & 16)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = nt * g.n_tile + cbase + j;
+            float o = v[j] + s_bias[cbase + j];
+            if (t_ok) {
+              if (d.skip_mode == VQVS_SKIP_IDENTITY) {
+                const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
+                                             : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
+                if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
+                else if (d.skip_resize == VQVS_RESIZE_UP2) o += __ldg(sp + (t >> 1));
+                else { const float2 p = __ldg(reinterpret_cast<const float2*>(sp + 2 * t)); o += 0.5f * (p.x + p.y); }
+              }
+              d.out[((size_t)n * d.c_out + co) * d.t_out + t] = o;
+            } else {
+              o = 0.f;
+            }
+            if (d.stats_out) {
+              const float s1 = warp_sum(o), s2 = warp_sum(o * o);
+              if (lane == 0) {
+                atomicAdd(s_stat + cbase + j, s1);
+                atomicAdd(s_stat + 256 + cbase + j, s2);
+              }
+            }
           }
         }
-        mma_commit(EMPTY(s));
       }
-      mma_commit(acc_full);
-      }  // tile loop
+      if (d.stats_out && !(d.reserved_ & 1)) {
+        // one fp64 atomic per (channel, statistic) and tile
+        asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
+        for (int i = etid; i < 2 * g.n_tile; i += EPI_WARPS * 32) {
+          const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
+          const float val = s_stat[which * 256 + c];
+          s_stat[which * 256 + c] = 0.f;
+          atomicAdd(d.stats_out + ((size_t)n * d.c_out + nt * g.n_tile + c) * 2 + which, (double)val);
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
+      }
     }
+    tc_fence_before();
   }
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -765,9 +819,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
 #undef TILE_COORDS
-#undef FULL_LD
-#undef FULL_A
-#undef EMPTY
+#undef RAW_FULL
+#undef RAW_EMPTY
+#undef B_FULL
+#undef A_FULL
+#undef AB_EMPTY
+#undef ACC_FULL
+#undef ACC_EMPTY
+#undef W_FULL
 }
 
 // ---------------------------------------------------------------------------
@@ -1033,9 +1092,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   g.tiles_t = ceil_div(d->t_out, umma::TILE_M);
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
-  const int ctas_per_sm = g.smem_bytes <= 113 * 1024 ? 2 : 1;
-  int grid = sm_count * ctas_per_sm;
-  if (grid > g.tiles_total) grid = g.tiles_total;
+  int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);
   grid = ceil_div(g.tiles_total, g.tiles_per_cta);
   umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
