@@ -446,6 +446,18 @@ __device__ __forceinline__ void transform_up2(const StageView& v, int chunk, int
   }
 }
 
+struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division on the critical path
+  int idx, n;
+  uint32_t ph;
+  __device__ __forceinline__ Ring(int slots) : idx(0), n(slots), ph(0) {}
+  __device__ __forceinline__ void next() {
+    if (++idx == n) {
+      idx = 0;
+      ph ^= 1;
+    }
+  }
+};
+
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
@@ -468,8 +480,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const int c_in = d.c_a + d.c_b;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_lo = blockIdx.x * g.tiles_per_cta;
-  const int tile_hi = min(tile_lo + g.tiles_per_cta, g.tiles_total);
+  // tile schedule: round-robin, so that concurrently running CTAs touch neighbouring time tiles
+  const int tile_first = (int)blockIdx.x, tile_stride = (int)gridDim.x;
+  const int n_my_tiles = (g.tiles_total - tile_first + tile_stride - 1) / tile_stride;
 #define TILE_COORDS(tile)                          \
   const int tx_ = (tile) % g.tiles_t;              \
   const int nt = ((tile) / g.tiles_t) % g.n_tiles; \
@@ -513,8 +526,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     // =========================== operand producers (transform warps) ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
-    int it = 0, staged_n = -1;
-    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
+    int staged_n = -1;
+    // this thread's fixed item of a row-wise stage
+    const int my_chunk = threadIdx.x >> 7, my_row = threadIdx.x & (TILE_M - 1);
+    for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+      const int tile = tile_first + k_local * tile_stride;
       TILE_COORDS(tile)
       (void)nt;
       if (d.act && n != staged_n) {  // per-sample GroupNorm/FiLM affine
@@ -524,31 +541,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         staged_n = n;
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
       }
-      for (int st = 0; st < total_k; ++st, ++it) {
-        const int s = it % g.ab_slots;
-        mbar_wait(AB_EMPTY(s), ((it / g.ab_slots) & 1) ^ 1);
-        const int r = g.tma ? it % g.raw_slots : 0;
+      StageView vm, vs;  // per-tile views of the main taps and of the 1x1 skip
+      vm.rows = vs.rows = g.rows;
+      vm.box_w = g.main_box_w;  vs.box_w = g.skip_box_w;
+      vm.boxes = g.main_boxes;  vs.boxes = 1;
+      vm.x0 = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
+      vs.x0 = (t0 * g.skip_origin_mul) / 2;
+      vm.tcs = t0 - g.pad;      vs.tcs = t0;
+      vm.n_rows = g.rows;       vs.n_rows = TILE_M;
+      vm.t_src = d.t_in;        vs.t_src = d.t_skip;
+      vm.t_conv = vs.t_conv = d.t_out;
+      vm.resize = d.resize;     vs.resize = d.skip_resize;
+      vm.act = d.act && !(d.reserved_ & 8);
+      vs.act = false;
+      for (int st = 0; st < total_k; ++st) {
+        mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
         const bool is_skip = st >= g.nkb_main;
         const int kb = is_skip ? st - g.nkb_main : st;
-        const int pad = is_skip ? 0 : g.pad;
-        uint8_t* a_slot = smem + g.off_ab + (size_t)s * g.ab_slot_bytes;
+        uint8_t* a_slot = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
         if (g.tma) {
-          mbar_wait(RAW_FULL(r), (it / g.raw_slots) & 1);
-          StageView v;
-          v.raw = reinterpret_cast<const float*>(smem + g.off_raw + (size_t)r * g.raw_slot_bytes);
+          mbar_wait(RAW_FULL(rw.idx), rw.ph);
+          StageView v = is_skip ? vs : vm;
+          v.raw = reinterpret_cast<const float*>(smem + g.off_raw + rw.idx * g.raw_slot_bytes);
           v.a = a_slot;
-          v.rows = g.rows;
-          v.box_w = is_skip ? g.skip_box_w : g.main_box_w;
-          v.boxes = is_skip ? 1 : g.main_boxes;
-          v.x0 = (t0 * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2 + (is_skip ? 0 : g.main_origin_off);
-          v.tcs = t0 - pad;
-          v.n_rows = TILE_M + 2 * pad;
-          v.t_src = is_skip ? d.t_skip : d.t_in;
-          v.t_conv = d.t_out;
-          v.resize = is_skip ? d.skip_resize : d.resize;
-          v.act = !is_skip && d.act && !(d.reserved_ & 8);
           v.ss = reinterpret_cast<const float4*>(s_ss + kb * KBLK);
-          if (v.resize == VQVS_RESIZE_UP2) {
+          if (d.reserved_ & 64) {
+            // ablation: no staging work at all
+          } else if (v.resize == VQVS_RESIZE_UP2) {
             const int first = v.tcs >> 1;
             const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
             for (int i = threadIdx.x; i < 2 * nsrc; i += XFORM_WARPS * 32) {
@@ -558,7 +577,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           } else {
             // warps 0..7: the 128 main rows of both chunks; last warp: the 2*pad halo rows
             if (warp < XFORM_WARPS - 1) {
-              transform_rowwise(v, threadIdx.x >> 7, threadIdx.x & (TILE_M - 1));
+              transform_rowwise(v, my_chunk, my_row);
             } else {
               const int n_extra = v.n_rows - TILE_M;
               for (int i = lane; i < 2 * n_extra; i += 32) {
@@ -570,6 +589,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         } else {
           const Src& src = is_skip ? skip_src : main_src;
           const bool act = !is_skip && d.act;
+          const int pad = is_skip ? 0 : g.pad;
           const int n_rows = TILE_M + 2 * pad;
           for (int i = threadIdx.x; i < 2 * n_rows; i += XFORM_WARPS * 32) {
             const int chunk = i >= n_rows, row = chunk ? i - n_rows : i;
@@ -581,33 +601,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(A_FULL(s));
-          if (g.tma) mbar_arrive(RAW_EMPTY(r));
+          mbar_arrive(A_FULL(ab.idx));
+          if (g.tma) mbar_arrive(RAW_EMPTY(rw.idx));
         }
+        ab.next();
+        rw.next();
       }
     }
   } else if (warp == TMA_RAW_WARP) {
     // =========================== TMA: raw activation boxes ===========================
     if (lane == 0 && g.tma) {
-      int it = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      Ring rw(g.raw_slots);
+      const uint32_t raw_base = smem_u32(smem + g.off_raw);
+      const uint32_t main_bytes = g.main_boxes * KBLK * g.main_box_w * 4, skip_bytes = KBLK * g.skip_box_w * 4;
+      const uint32_t box_bytes = KBLK * g.main_box_w * 4;
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+        const int tile = tile_first + k_local * tile_stride;
         TILE_COORDS(tile)
         (void)nt;
-        for (int st = 0; st < total_k; ++st, ++it) {
-          const int r = it % g.raw_slots;
-          mbar_wait(RAW_EMPTY(r), ((it / g.raw_slots) & 1) ^ 1);
-          const bool is_skip = st >= g.nkb_main;
-          const int kb = is_skip ? st - g.nkb_main : st;
-          const int box_w = is_skip ? g.skip_box_w : g.main_box_w;
-          const int boxes = is_skip ? 1 : g.main_boxes;
-          const int x0 = (t0 * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2 + (is_skip ? 0 : g.main_origin_off);
-          const int ca = is_skip ? d.s_a : d.c_a, cb = is_skip ? d.s_b : d.c_b;
-          const int c16 = kb * KBLK;
-          const CUtensorMap* map = c16 < ca ? (is_skip ? &tm_sa : &tm_xa) : (is_skip ? &tm_sb : &tm_xb);
-          const int rowc = c16 < ca ? n * ca + c16 : n * cb + (c16 - ca);
-          const uint32_t dst = smem_u32(smem + g.off_raw + (size_t)r * g.raw_slot_bytes);
-          mbar_expect_tx(RAW_FULL(r), boxes * KBLK * box_w * 4);
-          for (int b = 0; b < boxes; ++b) tma_box_2d(dst + b * (KBLK * box_w * 4), map, x0 + b * box_w, rowc, RAW_FULL(r));
+        const int x0m = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
+        const int x0s = (t0 * g.skip_origin_mul) / 2;
+        // main taps: channels [0, c_a) from xa, then [c_a, c_a+c_b) from xb
+        for (int c16 = 0; c16 < c_in; c16 += KBLK) {
+          mbar_wait(RAW_EMPTY(rw.idx), rw.ph ^ 1);
+          const bool from_a = c16 < d.c_a;
+          const CUtensorMap* map = from_a ? &tm_xa : &tm_xb;
+          const int rowc = from_a ? n * d.c_a + c16 : n * d.c_b + (c16 - d.c_a);
+          const uint32_t dst = raw_base + rw.idx * g.raw_slot_bytes;
+          mbar_expect_tx(RAW_FULL(rw.idx), main_bytes);
+          tma_box_2d(dst, map, x0m, rowc, RAW_FULL(rw.idx));
+          if (g.main_boxes == 2) tma_box_2d(dst + box_bytes, map, x0m + g.main_box_w, rowc, RAW_FULL(rw.idx));
+          rw.next();
+        }
+        const int c_skip = g.nkb_skip * KBLK;
+        for (int c16 = 0; c16 < c_skip; c16 += KBLK) {
+          mbar_wait(RAW_EMPTY(rw.idx), rw.ph ^ 1);
+          const bool from_a = c16 < d.s_a;
+          const CUtensorMap* map = from_a ? &tm_sa : &tm_sb;
+          const int rowc = from_a ? n * d.s_a + c16 : n * d.s_b + (c16 - d.s_a);
+          mbar_expect_tx(RAW_FULL(rw.idx), skip_bytes);
+          tma_box_2d(raw_base + rw.idx * g.raw_slot_bytes, map, x0s, rowc, RAW_FULL(rw.idx));
+          rw.next();
         }
       }
     }
@@ -623,20 +657,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           tma_bulk_g2s(smem_u32(smem + g.off_w + o), wimg + o, nbytes, W_FULL);
         }
       } else {
-        int it = 0;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
-          TILE_COORDS(tile)
-          (void)n; (void)t0;
-          const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
-          for (int st = 0; st < total_k; ++st, ++it) {
-            const int s = it % g.ab_slots;
-            mbar_wait(AB_EMPTY(s), ((it / g.ab_slots) & 1) ^ 1);
-            const bool is_skip = st >= g.nkb_main;
-            const uint32_t unit = is_skip ? g.b_unit_skip : g.b_unit_main;
-            const uint8_t* src = is_skip ? wimg + (size_t)g.nkb_main * g.b_unit_main + (size_t)(st - g.nkb_main) * g.b_unit_skip
-                                         : wimg + (size_t)st * g.b_unit_main;
-            mbar_expect_tx(B_FULL(s), unit);
-            tma_bulk_g2s(smem_u32(smem + g.off_ab + (size_t)s * g.ab_slot_bytes + g.a_kb_bytes), src, unit, B_FULL(s));
+        Ring ab(g.ab_slots);
+        const uint32_t b_base = smem_u32(smem + g.off_ab + g.a_kb_bytes);
+        for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+          const int tile = tile_first + k_local * tile_stride;
+          const int nt = (tile / g.tiles_t) % g.n_tiles;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
+          for (int st = 0; st < total_k; ++st) {
+            mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
+            const uint32_t unit = st >= g.nkb_main ? g.b_unit_skip : g.b_unit_main;
+            mbar_expect_tx(B_FULL(ab.idx), unit);
+            tma_bulk_g2s(b_base + ab.idx * g.ab_slot_bytes, src, unit, B_FULL(ab.idx));
+            src += unit;  // the image is laid out in pipeline order
+            ab.next();
           }
         }
       }
@@ -645,45 +678,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(g.n_tile);
-      const uint32_t a_lbo = g.rows * 16, b_lbo = g.n_tile * 16;
+      // descriptor = constant fields + (address >> 4); the address field never carries into LBO
+      const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
+      const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
+      const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
+      const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
+      const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
+      const uint32_t a_kb16 = g.a_kb_bytes >> 4;
       if (g.w_resident) mbar_wait(W_FULL, 0);
-      int it = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const int k_local = tile - tile_lo, buf = k_local & 1;
+      Ring ab(g.ab_slots);
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+        const int buf = k_local & 1;
         mbar_wait(ACC_EMPTY(buf), ((k_local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * g.acc_cols;
         uint32_t acc = 0;
-        for (int st = 0; st < total_k; ++st, ++it) {
-          const int s = it % g.ab_slots;
-          const uint32_t ph = (it / g.ab_slots) & 1;
-          mbar_wait(A_FULL(s), ph);
-          if (!g.w_resident) mbar_wait(B_FULL(s), ph);
+        uint32_t w16 = w_base16;
+        for (int st = 0; st < total_k; ++st) {
+          mbar_wait(A_FULL(ab.idx), ab.ph);
+          if (!g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
           tc_fence_after();
           const bool is_skip = st >= g.nkb_main;
-          const uint32_t a_hi = smem_u32(smem + g.off_ab + (size_t)s * g.ab_slot_bytes);
-          const uint32_t a_lo = a_hi + g.rows * 32;
-          uint32_t b_unit;
-          if (g.w_resident)
-            b_unit = smem_u32(smem + g.off_w) + (is_skip ? g.nkb_main * g.b_unit_main + (st - g.nkb_main) * g.b_unit_skip : st * g.b_unit_main);
-          else
-            b_unit = a_hi + g.a_kb_bytes;
+          const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
+          const uint32_t b16 = g.w_resident ? w16 : a16 + a_kb16;
+          w16 += is_skip ? unit_skip16 : unit_main16;
           const int taps = is_skip ? 1 : d.ksize;
-          for (int tap = 0; tap < taps; ++tap) {
-            if (d.reserved_ & 4) continue;
-            const uint32_t shift = is_skip ? 0u : (uint32_t)(tap * d.dilation * 16);
-            const uint32_t b_hi = b_unit + tap * (g.n_tile * 64);
-            const uint32_t b_lo = b_hi + g.n_tile * 32;
-            const uint64_t da_hi = make_desc(a_hi + shift, a_lbo, 128);
-            const uint64_t da_lo = make_desc(a_lo + shift, a_lbo, 128);
-            const uint64_t db_hi = make_desc(b_hi, b_lbo, 128);
-            const uint64_t db_lo = make_desc(b_lo, b_lbo, 128);
-            mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
-            acc = 1;
-            mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
-            mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+          const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
+          if (!(d.reserved_ & 4)) {
+#pragma unroll 3
+            for (int tap = 0; tap < taps; ++tap) {
+              const uint64_t da_hi = a_const + (a16 + tap * tap_rows);
+              const uint64_t db_hi = b_const + (b16 + tap * b_tap_off);
+              mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
+              acc = 1;
+              mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
+              mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+            }
           }
-          mma_commit(AB_EMPTY(s));
+          mma_commit(AB_EMPTY(ab.idx));
+          ab.next();
         }
         mma_commit(ACC_FULL(buf));
       }
@@ -693,7 +726,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
     const int etid = threadIdx.x - EPI_WARP0 * 32;
     int staged_nt = -1;
-    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+      const int tile = tile_first + k_local * tile_stride;
       TILE_COORDS(tile)
       if (nt != staged_nt) {  // bias slice of this N tile
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
@@ -706,7 +740,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         staged_nt = nt;
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
       }
-      const int k_local = tile - tile_lo, buf = k_local & 1;
+      const int buf = k_local & 1;
       mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
       tc_fence_after();
       const uint32_t acc_addr = tmem_base + buf * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
