@@ -261,6 +261,10 @@ int vqvs_run(const VqvsOp* ops, int n_ops, void* stream);
  * in milliseconds (synchronises the stream at the end; measurement aid for bench.py). */
 int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 
+/* Role profiler of the last vqvs_conv1d_umma launched with debug flag 512 (cycles per phase of CTA 0):
+ * [0..3] transform warp 0: wait operand slot, wait raw, work, loop; [4..7] TMA; [8..11] MMA; [12..15] epilogue. */
+int vqvs_debug_prof(unsigned long long* host32);
+
 /* tcgen05 self-test: runs D[128,n] = A[128,k] * B[n,k]^T through the exact smem layout,
  * descriptors and TMEM read-back used by vqvs_conv1d_umma, with A rows shifted by `row_shift`.
  * a: [128+row_shift, k] fp32, b: [n, k] fp32, d: [128, n] fp32 (device).

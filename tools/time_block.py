@@ -19,3 +19,9 @@ for _ in range(5):
     L.check(L.load().vqvs_run_timed(plan.ops, n, L.stream_ptr(), buf))
     for i in range(n): acc[i] += buf[i] / 5
 print(" ".join("%s=%.3fms" % ({2: "umma", 1: "simt", 3: "gn"}[k], ms) for (k, _), ms in zip(plan.descs, acc)))
+
+if int(os.environ.get("VQVS_DEBUG_FLAGS", "0")) & 512:
+    buf = (C.c_uint64 * 32)()
+    L.check(L.load().vqvs_debug_prof(buf))
+    names = ["xf.wait_ab", "xf.wait_raw", "xf.work", "xf.loop", "tma.wait_empty", "tma.issue", "tma.-", "tma.-", "mma.wait_a", "mma.issue", "mma.wait_acc", "mma.loop", "epi.wait_full", "epi.work", "epi.-", "epi.-"]
+    print(" | ".join("%s=%d" % (n, buf[i]) for i, n in enumerate(names) if buf[i]))

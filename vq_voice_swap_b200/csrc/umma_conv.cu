@@ -35,10 +35,12 @@ constexpr int XFORM_WARPS = 9;    // 8 warps transform the 128 main rows x 2 chu
 constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
 constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
 constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
-constexpr int EPI_WARP0 = 12;     // warps 12..15 <-> TMEM lane quarters 0..3
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARP0 = 12;     // warps 12..19 <-> TMEM lane quarters (warp & 3)
+constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
-constexpr int SMEM_HEADER = 384;  // 33 mbarriers + TMEM base holder
+constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
+constexpr int MAX_RAW_SLOTS = 16;
+constexpr int MAX_AB_SLOTS = 8;
 
 // Host-computed geometry shared by the packer and the kernel.
 struct Geo {
@@ -52,8 +54,11 @@ struct Geo {
   long long per_tile_bytes; // packed weight image bytes per N tile
   // shared-memory plan (byte offsets from the dynamic smem base)
   int off_stat, off_ss, off_bias, off_w, off_raw, off_ab;
+  int kbs;                        // K blocks per pipeline stage (2 when the rings still fit, else 1)
+  int raw_kb_bytes;               // raw staging bytes of ONE K block (a slot holds kbs of them)
   int raw_slot_bytes, raw_slots;  // fp32 staging ring filled by TMA (0 slots in direct mode)
-  int ab_slot_bytes, ab_slots;    // operand ring: A tile (+ streamed weights of the K block)
+  int ab_slot_bytes, ab_slots;    // operand ring: kbs A tiles (+ the streamed weights of those K blocks)
+  int main_stages, skip_stages;
   int w_resident;                 // 1: the whole weight image of the N tile stays in smem for all tiles of the CTA
   int smem_bytes;
   // TMA activation boxes, in SOURCE coordinates relative to the tile origin
@@ -109,9 +114,10 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     g->raw_slot_bytes = KBLK * widest * 4;
   }
   // ---- shared-memory plan: one persistent CTA per SM -----------------------------------------
+  g->raw_kb_bytes = g->raw_slot_bytes;
   const int budget = 225 * 1024;
   int off = SMEM_HEADER;
-  g->off_stat = off; off += 2 * 256 * 4;
+  g->off_stat = off;
   g->off_ss = off;   off += c_in * 8;
   g->off_bias = off; off += g->n_tile * 4;
   off = align_up(off, 128);
@@ -120,21 +126,35 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->w_resident = (g->n_tiles == 1 && w_img <= 100 * 1024) ? 1 : 0;
   if (g->w_resident) off += (int)w_img;
   g->off_raw = off;
-  const int b_slot = g->w_resident ? 0 : g->b_unit_main;
-  g->ab_slot_bytes = g->a_kb_bytes + b_slot;
-  int left = budget - off;
-  // operand ring first (2..4 slots), the rest of the budget is raw prefetch depth (<= 8 slots)
-  int ab = 4;
-  while (ab > 2 && left - ab * g->ab_slot_bytes < (tma ? 3 * g->raw_slot_bytes : 0)) --ab;
-  if (left < ab * g->ab_slot_bytes + (tma ? 2 * g->raw_slot_bytes : 0)) return false;
-  g->ab_slots = ab;
-  left -= ab * g->ab_slot_bytes;
-  int raw = tma ? left / g->raw_slot_bytes : 0;
-  g->raw_slots = raw > 8 ? 8 : raw;
+  const int left0 = budget - off;
+  bool ok = false;
+  for (int kbs = 2; kbs >= 1 && !ok; --kbs) {
+    const int ab_slot = kbs * (g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
+    const int raw_slot = kbs * g->raw_kb_bytes;
+    const int min_ab = 2, min_raw = tma ? 3 : 0;
+    if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
+    if (kbs == 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
+    int ab = MAX_AB_SLOTS;
+    while (ab > min_ab && left0 - ab * ab_slot < (tma ? 4 * raw_slot : 0)) --ab;
+    if (left0 - ab * ab_slot < min_raw * raw_slot) continue;
+    if (ab > 4) ab = 4;
+    int raw = tma ? (left0 - ab * ab_slot) / raw_slot : 0;
+    if (raw > MAX_RAW_SLOTS) raw = MAX_RAW_SLOTS;
+    if (raw > 8) raw = 8;
+    g->kbs = kbs;
+    g->ab_slot_bytes = ab_slot;
+    g->ab_slots = ab;
+    g->raw_slot_bytes = raw_slot;
+    g->raw_slots = raw;
+    ok = true;
+  }
+  if (!ok) return false;
   off += g->raw_slots * g->raw_slot_bytes;
   g->off_ab = off;
   off += g->ab_slots * g->ab_slot_bytes;
   g->smem_bytes = off;
+  g->main_stages = (g->nkb_main + g->kbs - 1) / g->kbs;
+  g->skip_stages = (g->nkb_skip + g->kbs - 1) / g->kbs;
   g->tiles_t = g->tiles_total = g->tiles_per_cta = 0;  // filled at launch
   return true;
 }
@@ -370,70 +390,88 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-// Transform one item: 8 channels (one 16-B operand chunk) at conv position(s) -> bf16 hi/lo rows.
+// Per-tile description of one operand source (main taps or 1x1 skip) in TMA mode.
 struct StageView {
-  const float* raw;   // raw slot (TMA mode)
-  uint8_t* a;         // operand slot
   int rows;           // operand rows of this conv (row pitch of the hi/lo blocks)
   int box_w, boxes, x0, tcs, n_rows, t_src, t_conv, resize;
   bool act;
-  const float4* ss;   // (scale, shift) pairs of the 16 channels of this K block
 };
 
-__device__ __forceinline__ void transform_rowwise(const StageView& v, int chunk, int row) {
+// Row-wise item: the same (8-channel chunk, row) of NK consecutive K blocks -> bf16 hi/lo operand rows.
+// raw / a / ss point at the first K block; the others follow at raw_kb / a_kb bytes and 16 channels.
+template <int NK>
+__device__ __forceinline__ void transform_rowwise(const StageView& v, const uint8_t* raw0, int raw_kb, uint8_t* a0, int a_kb,
+                                                  const float2* ss0, int chunk, int row) {
   const int tc = v.tcs + row;
-  float x[8];
+  float x[NK][8];
   if (tc >= 0 && tc < v.t_conv) {
     if (v.resize != VQVS_RESIZE_DOWN2) {
-      const float* raw = v.raw + (chunk * 8) * v.box_w + (tc - v.x0);
+      const int o = (chunk * 8) * v.box_w + (tc - v.x0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
-      if (v.act) affine_gelu8(x, v.ss + chunk * 4);
-    } else {
-      int col = 2 * tc - v.x0;
-      const float* raw = v.raw;
-      if (v.boxes == 2 && col >= v.box_w) {
-        col -= v.box_w;
-        raw += KBLK * v.box_w;
-      }
-      raw += (chunk * 8) * v.box_w + col;
-      float w[8];
+      for (int k = 0; k < NK; ++k) {
+        const float* raw = reinterpret_cast<const float*>(raw0 + k * raw_kb) + o;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float2 p = *reinterpret_cast<const float2*>(raw + e * v.box_w);
-        x[e] = p.x;
-        w[e] = p.y;
+        for (int e = 0; e < 8; ++e) x[k][e] = raw[e * v.box_w];
       }
       if (v.act) {
-        affine_gelu8(x, v.ss + chunk * 4);
-        affine_gelu8(w, v.ss + chunk * 4);
-      }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = 0.5f * (x[e] + w[e]);
+        for (int k = 0; k < NK; ++k) affine_gelu8(x[k], reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
+      }
+    } else {
+      int col = 2 * tc - v.x0;
+      int o = (chunk * 8) * v.box_w;
+      if (v.boxes == 2 && col >= v.box_w) {
+        col -= v.box_w;
+        o += KBLK * v.box_w;
+      }
+      o += col;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const float* raw = reinterpret_cast<const float*>(raw0 + k * raw_kb) + o;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 p = *reinterpret_cast<const float2*>(raw + e * v.box_w);
+          x[k][e] = p.x;
+          w[e] = p.y;
+        }
+        if (v.act) {
+          affine_gelu8(x[k], reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
+          affine_gelu8(w, reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[k][e] = 0.5f * (x[k][e] + w[e]);
+      }
     }
   } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[k][e] = 0.f;
   }
-  uint8_t* a_hi = v.a + chunk * (v.rows * 16);
-  store_rows(x, a_hi, a_hi + v.rows * 32, row);
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    uint8_t* a_hi = a0 + k * a_kb + chunk * (v.rows * 16);
+    store_rows(x[k], a_hi, a_hi + v.rows * 32, row);
+  }
 }
 
-// nearest x2: one item = one SOURCE position -> two operand rows (GELU evaluated once)
-__device__ __forceinline__ void transform_up2(const StageView& v, int chunk, int ts) {
+// nearest x2: one item = one SOURCE position of one K block -> two operand rows (GELU evaluated once)
+__device__ __forceinline__ void transform_up2(const StageView& v, const uint8_t* raw_k, uint8_t* a_k, const float2* ss_k,
+                                              int chunk, int ts) {
   float x[8];
   if (ts >= 0 && ts < v.t_src) {
-    const float* raw = v.raw + (chunk * 8) * v.box_w + (ts - v.x0);
+    const float* raw = reinterpret_cast<const float*>(raw_k) + (chunk * 8) * v.box_w + (ts - v.x0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
-    if (v.act) affine_gelu8(x, v.ss + chunk * 4);
+    if (v.act) affine_gelu8(x, reinterpret_cast<const float4*>(ss_k + chunk * 8));
   } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = 0.f;
   }
   uint4 hi, lo;
   split8(x, &hi, &lo);
-  uint8_t* a_hi = v.a + chunk * (v.rows * 16);
+  uint8_t* a_hi = a_k + chunk * (v.rows * 16);
   uint8_t* a_lo = a_hi + v.rows * 32;
   const int r0 = 2 * ts - v.tcs;
   if (r0 >= 0 && r0 < v.n_rows) {
@@ -445,6 +483,23 @@ __device__ __forceinline__ void transform_up2(const StageView& v, int chunk, int
     *reinterpret_cast<uint4*>(a_lo + (r0 + 1) * 16) = lo;
   }
 }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Optional role profiler (debug flag 512): cycles per phase of block 0, read back with vqvs_debug_prof.
+__device__ unsigned long long g_prof[32];
+#define PROF_T0() const long long p0_ = prof ? clock64() : 0
+#define PROF_ADD(slot, since) do { if (prof) { const long long now_ = clock64(); acc_[slot] += now_ - (since); (since) = now_; } } while (0)
 
 struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division on the critical path
   int idx, n;
@@ -463,18 +518,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // mbarriers: raw_full[8] raw_empty[8] b_full[4] a_full[4] ab_empty[4] acc_full[2] acc_empty[2] w_full
+  // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
 #define RAW_FULL(i) (bar0 + 8u * (i))
-#define RAW_EMPTY(i) (bar0 + 8u * (8 + (i)))
-#define B_FULL(i) (bar0 + 8u * (16 + (i)))
-#define A_FULL(i) (bar0 + 8u * (20 + (i)))
-#define AB_EMPTY(i) (bar0 + 8u * (24 + (i)))
-#define ACC_FULL(i) (bar0 + 8u * (28 + (i)))
-#define ACC_EMPTY(i) (bar0 + 8u * (30 + (i)))
-#define W_FULL (bar0 + 8u * 32)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 33 * 8);
-  float* s_stat = reinterpret_cast<float*>(smem + g.off_stat);  // [2][256] per-tile (sum, sumsq) combine
+#define RAW_EMPTY(i) (bar0 + 8u * (16 + (i)))
+#define B_FULL(i) (bar0 + 8u * (32 + (i)))
+#define A_FULL(i) (bar0 + 8u * (40 + (i)))
+#define AB_EMPTY(i) (bar0 + 8u * (48 + (i)))
+#define ACC_FULL(i) (bar0 + 8u * (56 + (i)))
+#define ACC_EMPTY(i) (bar0 + 8u * (58 + (i)))
+#define W_FULL (bar0 + 8u * 60)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 61 * 8);
   float2* s_ss = reinterpret_cast<float2*>(smem + g.off_ss);    // (scale, shift) of the current sample
   float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
   const int c_in = d.c_a + d.c_b;
@@ -490,11 +544,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const int t0 = tx_ * TILE_M;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MAX_RAW_SLOTS; ++i) {
       mbar_init(RAW_FULL(i), 1);
       mbar_init(RAW_EMPTY(i), XFORM_WARPS);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MAX_AB_SLOTS; ++i) {
       mbar_init(B_FULL(i), 1);
       mbar_init(A_FULL(i), XFORM_WARPS);
       mbar_init(AB_EMPTY(i), 1);
@@ -515,12 +569,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       if (d.s_b) tma_prefetch_desc(&tm_sb);
     }
   }
-  for (int i = threadIdx.x; i < 2 * 256; i += THREADS) s_stat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const int total_k = g.nkb_main + g.nkb_skip;  // pipeline steps (K blocks) per tile
+  const int total_stages = g.main_stages + g.skip_stages;
 
   if (warp < XFORM_WARPS) {
     // =========================== operand producers (transform warps) ===========================
@@ -528,6 +581,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
+    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && threadIdx.x == 0;
+    long long acc_[4] = {0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
     // this thread's fixed item of a row-wise stage
     const int my_chunk = threadIdx.x >> 7, my_row = threadIdx.x & (TILE_M - 1);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
@@ -554,35 +610,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       vm.resize = d.resize;     vs.resize = d.skip_resize;
       vm.act = d.act && !(d.reserved_ & 8);
       vs.act = false;
-      for (int st = 0; st < total_k; ++st) {
+      for (int st = 0; st < total_stages; ++st) {
+        PROF_ADD(3, tprev);
         mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
-        const bool is_skip = st >= g.nkb_main;
-        const int kb = is_skip ? st - g.nkb_main : st;
+        PROF_ADD(0, tprev);
+        const bool is_skip = st >= g.main_stages;
+        const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
+        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         uint8_t* a_slot = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
         if (g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
-          StageView v = is_skip ? vs : vm;
-          v.raw = reinterpret_cast<const float*>(smem + g.off_raw + rw.idx * g.raw_slot_bytes);
-          v.a = a_slot;
-          v.ss = reinterpret_cast<const float4*>(s_ss + kb * KBLK);
+          PROF_ADD(1, tprev);
+          const StageView& v = is_skip ? vs : vm;
+          const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes;
+          const float2* ss = s_ss + kb0 * KBLK;
           if (d.reserved_ & 64) {
             // ablation: no staging work at all
           } else if (v.resize == VQVS_RESIZE_UP2) {
             const int first = v.tcs >> 1;
             const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
-            for (int i = threadIdx.x; i < 2 * nsrc; i += XFORM_WARPS * 32) {
-              const int chunk = i >= nsrc, j = chunk ? i - nsrc : i;
-              transform_up2(v, chunk, first + j);
+            for (int i = threadIdx.x; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
+              const int q = i / nsrc, j = i - q * nsrc;  // q = (k block, chunk)
+              transform_up2(v, raw + (q >> 1) * g.raw_kb_bytes, a_slot + (q >> 1) * g.a_kb_bytes, ss + (q >> 1) * KBLK, q & 1, first + j);
             }
           } else {
-            // warps 0..7: the 128 main rows of both chunks; last warp: the 2*pad halo rows
+            // warps 0..7: the 128 main rows of both chunks (all K blocks of the stage); last warp: the halo rows
             if (warp < XFORM_WARPS - 1) {
-              transform_rowwise(v, my_chunk, my_row);
+              if (nk == 2) transform_rowwise<2>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
+              else transform_rowwise<1>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
             } else {
               const int n_extra = v.n_rows - TILE_M;
               for (int i = lane; i < 2 * n_extra; i += 32) {
                 const int chunk = i >= n_extra;
-                transform_rowwise(v, chunk, TILE_M + (chunk ? i - n_extra : i));
+                const int row = TILE_M + (chunk ? i - n_extra : i);
+                if (nk == 2) transform_rowwise<2>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, chunk, row);
+                else transform_rowwise<1>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, chunk, row);
               }
             }
           }
@@ -591,10 +653,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const bool act = !is_skip && d.act;
           const int pad = is_skip ? 0 : g.pad;
           const int n_rows = TILE_M + 2 * pad;
-          for (int i = threadIdx.x; i < 2 * n_rows; i += XFORM_WARPS * 32) {
-            const int chunk = i >= n_rows, row = chunk ? i - n_rows : i;
-            const int c8 = kb * KBLK + chunk * 8;
-            uint8_t* a_hi = a_slot + chunk * (g.rows * 16);
+          for (int i = threadIdx.x; i < nk * 2 * n_rows; i += XFORM_WARPS * 32) {
+            const int q = i / n_rows, row = i - q * n_rows;
+            const int c8 = kb0 * KBLK + q * 8;
+            uint8_t* a_hi = a_slot + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
             produce_direct(src, n, c8, t0 - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
           }
         }
@@ -606,14 +668,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
         ab.next();
         rw.next();
+        PROF_ADD(2, tprev);
       }
     }
+    if (prof) for (int i = 0; i < 4; ++i) g_prof[i] = acc_[i];
   } else if (warp == TMA_RAW_WARP) {
-    // =========================== TMA: raw activation boxes ===========================
-    if (lane == 0 && g.tma) {
+    // =========================== TMA: raw activation boxes (warp-uniform loop, elected issue) ==========
+    if (g.tma) {
       Ring rw(g.raw_slots);
       const uint32_t raw_base = smem_u32(smem + g.off_raw);
-      const uint32_t main_bytes = g.main_boxes * KBLK * g.main_box_w * 4, skip_bytes = KBLK * g.skip_box_w * 4;
       const uint32_t box_bytes = KBLK * g.main_box_w * 4;
       for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
         const int tile = tile_first + k_local * tile_stride;
@@ -621,34 +684,44 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         (void)nt;
         const int x0m = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
         const int x0s = (t0 * g.skip_origin_mul) / 2;
-        // main taps: channels [0, c_a) from xa, then [c_a, c_a+c_b) from xb
-        for (int c16 = 0; c16 < c_in; c16 += KBLK) {
+        for (int st = 0; st < total_stages; ++st) {
+          const bool is_skip = st >= g.main_stages;
+          const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
+          const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
           mbar_wait(RAW_EMPTY(rw.idx), rw.ph ^ 1);
-          const bool from_a = c16 < d.c_a;
-          const CUtensorMap* map = from_a ? &tm_xa : &tm_xb;
-          const int rowc = from_a ? n * d.c_a + c16 : n * d.c_b + (c16 - d.c_a);
-          const uint32_t dst = raw_base + rw.idx * g.raw_slot_bytes;
-          mbar_expect_tx(RAW_FULL(rw.idx), main_bytes);
-          tma_box_2d(dst, map, x0m, rowc, RAW_FULL(rw.idx));
-          if (g.main_boxes == 2) tma_box_2d(dst + box_bytes, map, x0m + g.main_box_w, rowc, RAW_FULL(rw.idx));
-          rw.next();
-        }
-        const int c_skip = g.nkb_skip * KBLK;
-        for (int c16 = 0; c16 < c_skip; c16 += KBLK) {
-          mbar_wait(RAW_EMPTY(rw.idx), rw.ph ^ 1);
-          const bool from_a = c16 < d.s_a;
-          const CUtensorMap* map = from_a ? &tm_sa : &tm_sb;
-          const int rowc = from_a ? n * d.s_a + c16 : n * d.s_b + (c16 - d.s_a);
-          mbar_expect_tx(RAW_FULL(rw.idx), skip_bytes);
-          tma_box_2d(raw_base + rw.idx * g.raw_slot_bytes, map, x0s, rowc, RAW_FULL(rw.idx));
+          if (elect_one()) {
+            const uint32_t dst0 = raw_base + rw.idx * g.raw_slot_bytes;
+            if (!is_skip) {
+              mbar_expect_tx(RAW_FULL(rw.idx), nk * g.main_boxes * box_bytes);
+              for (int k = 0; k < nk; ++k) {
+                const int c16 = (kb0 + k) * KBLK;
+                const bool from_a = c16 < d.c_a;
+                const CUtensorMap* map = from_a ? &tm_xa : &tm_xb;
+                const int rowc = from_a ? n * d.c_a + c16 : n * d.c_b + (c16 - d.c_a);
+                const uint32_t dst = dst0 + k * g.raw_kb_bytes;
+                tma_box_2d(dst, map, x0m, rowc, RAW_FULL(rw.idx));
+                if (g.main_boxes == 2) tma_box_2d(dst + box_bytes, map, x0m + g.main_box_w, rowc, RAW_FULL(rw.idx));
+              }
+            } else {
+              mbar_expect_tx(RAW_FULL(rw.idx), nk * KBLK * g.skip_box_w * 4);
+              for (int k = 0; k < nk; ++k) {
+                const int c16 = (kb0 + k) * KBLK;
+                const bool from_a = c16 < d.s_a;
+                const CUtensorMap* map = from_a ? &tm_sa : &tm_sb;
+                const int rowc = from_a ? n * d.s_a + c16 : n * d.s_b + (c16 - d.s_a);
+                tma_box_2d(dst0 + k * g.raw_kb_bytes, map, x0s, rowc, RAW_FULL(rw.idx));
+              }
+            }
+          }
+          __syncwarp();
           rw.next();
         }
       }
     }
   } else if (warp == TMA_W_WARP) {
     // =========================== TMA: weight image ===========================
-    if (lane == 0) {
-      if (g.w_resident) {  // loaded once, reused by every tile of this CTA
+    if (g.w_resident) {  // loaded once, reused by every tile of this CTA
+      if (elect_one()) {
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed);
         const uint32_t total = (uint32_t)g.per_tile_bytes;
         mbar_expect_tx(W_FULL, total);
@@ -656,76 +729,118 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const uint32_t nbytes = total - o < 32768 ? total - o : 32768;
           tma_bulk_g2s(smem_u32(smem + g.off_w + o), wimg + o, nbytes, W_FULL);
         }
-      } else {
-        Ring ab(g.ab_slots);
-        const uint32_t b_base = smem_u32(smem + g.off_ab + g.a_kb_bytes);
-        for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-          const int tile = tile_first + k_local * tile_stride;
-          const int nt = (tile / g.tiles_t) % g.n_tiles;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
-          for (int st = 0; st < total_k; ++st) {
-            mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
-            const uint32_t unit = st >= g.nkb_main ? g.b_unit_skip : g.b_unit_main;
-            mbar_expect_tx(B_FULL(ab.idx), unit);
-            tma_bulk_g2s(b_base + ab.idx * g.ab_slot_bytes, src, unit, B_FULL(ab.idx));
-            src += unit;  // the image is laid out in pipeline order
-            ab.next();
+      }
+    } else {
+      Ring ab(g.ab_slots);
+      const uint32_t b_base = smem_u32(smem + g.off_ab + g.kbs * g.a_kb_bytes);
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+        const int tile = tile_first + k_local * tile_stride;
+        const int nt = (tile / g.tiles_t) % g.n_tiles;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
+        for (int st = 0; st < total_stages; ++st) {
+          const bool is_skip = st >= g.main_stages;
+          const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
+          const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
+          const uint32_t bytes = nk * (is_skip ? g.b_unit_skip : g.b_unit_main);
+          mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(B_FULL(ab.idx), bytes);
+            tma_bulk_g2s(b_base + ab.idx * g.ab_slot_bytes, src, bytes, B_FULL(ab.idx));
           }
+          __syncwarp();
+          src += bytes;  // the image is laid out in pipeline order
+          ab.next();
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(g.n_tile);
-      // descriptor = constant fields + (address >> 4); the address field never carries into LBO
-      const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
-      const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
-      const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
-      const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
-      const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
-      const uint32_t a_kb16 = g.a_kb_bytes >> 4;
-      if (g.w_resident) mbar_wait(W_FULL, 0);
-      Ring ab(g.ab_slots);
-      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-        const int buf = k_local & 1;
-        mbar_wait(ACC_EMPTY(buf), ((k_local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+    // =========================== MMA issuer (warp-uniform loop, elected issue) ===========================
+    const uint32_t idesc = make_idesc(g.n_tile);
+    // descriptor = constant fields + (address >> 4); the address field never carries into LBO
+    const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
+    const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
+    const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
+    const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
+    const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
+    const uint32_t a_kb16 = g.a_kb_bytes >> 4;
+    if (g.w_resident) mbar_wait(W_FULL, 0);
+    Ring ab(g.ab_slots);
+    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && lane == 0;
+    long long acc_[4] = {0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
+    for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
+      const int buf = k_local & 1;
+      PROF_ADD(3, tprev);
+      mbar_wait(ACC_EMPTY(buf), ((k_local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      PROF_ADD(2, tprev);
+      const uint32_t d_tmem = tmem_base + buf * g.acc_cols;
+      uint32_t acc = 0;
+      uint32_t w16 = w_base16;
+      for (int st = 0; st < total_stages; ++st) {
+        PROF_ADD(1, tprev);
+        mbar_wait(A_FULL(ab.idx), ab.ph);
+        if (!g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * g.acc_cols;
-        uint32_t acc = 0;
-        uint32_t w16 = w_base16;
-        for (int st = 0; st < total_k; ++st) {
-          mbar_wait(A_FULL(ab.idx), ab.ph);
-          if (!g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
-          tc_fence_after();
-          const bool is_skip = st >= g.nkb_main;
-          const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
-          const uint32_t b16 = g.w_resident ? w16 : a16 + a_kb16;
-          w16 += is_skip ? unit_skip16 : unit_main16;
-          const int taps = is_skip ? 1 : d.ksize;
-          const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
+        PROF_ADD(0, tprev);
+        const bool is_skip = st >= g.main_stages;
+        const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
+        const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
+        const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
+        const uint32_t unit16 = is_skip ? unit_skip16 : unit_main16;
+        const uint32_t b16 = g.w_resident ? w16 : a16 + g.kbs * a_kb16;
+        w16 += nk * unit16;
+        const int taps = is_skip ? 1 : d.ksize;
+        const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
+        if (elect_one()) {
           if (!(d.reserved_ & 4)) {
+            for (int k = 0; k < nk; ++k) {
 #pragma unroll 3
-            for (int tap = 0; tap < taps; ++tap) {
-              const uint64_t da_hi = a_const + (a16 + tap * tap_rows);
-              const uint64_t db_hi = b_const + (b16 + tap * b_tap_off);
-              mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
-              acc = 1;
-              mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
-              mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+              for (int tap = 0; tap < taps; ++tap) {
+                const uint64_t da_hi = a_const + (a16 + k * a_kb16 + tap * tap_rows);
+                const uint64_t db_hi = b_const + (b16 + k * unit16 + tap * b_tap_off);
+                mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
+                acc = 1;
+                mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
+                mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+              }
             }
           }
           mma_commit(AB_EMPTY(ab.idx));
-          ab.next();
+          if (st == total_stages - 1) mma_commit(ACC_FULL(buf));
         }
-        mma_commit(ACC_FULL(buf));
+        __syncwarp();
+        acc = 1;
+        ab.next();
       }
     }
+    if (prof) for (int i = 0; i < 4; ++i) g_prof[8 + i] = acc_[i];
   } else {
     // =========================== epilogue warps ===========================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
+    const int quarter = warp & 3;              // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = (warp - EPI_WARP0) >> 2;  // the two warps of a quarter take alternate 32-column chunks
     const int etid = threadIdx.x - EPI_WARP0 * 32;
-    int staged_nt = -1;
+    int staged_nt = -1, stat_n = -1, stat_nt = 0;
+    // running per-channel (sum, sumsq) of this warp's rows for up to 4 chunks, flushed when the sample changes
+    double rs1[4] = {0, 0, 0, 0}, rs2[4] = {0, 0, 0, 0};
+    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && etid == 0;
+    long long acc_[4] = {0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
+    const int n_chunks32 = g.n_tile / 32;
+    const bool tail16 = (g.n_tile & 31) != 0;
+    const bool stats = d.stats_out && !(d.reserved_ & 1);
+    auto flush_stats = [&](int fn, int fnt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = half + 2 * i;
+        if (ch < n_chunks32) {
+          double* st = d.stats_out + ((size_t)fn * d.c_out + fnt * g.n_tile + ch * 32 + lane) * 2;
+          atomicAdd(st, rs1[i]);
+          atomicAdd(st + 1, rs2[i]);
+          rs1[i] = rs2[i] = 0.0;
+        }
+      }
+    };
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
       const int tile = tile_first + k_local * tile_stride;
       TILE_COORDS(tile)
@@ -740,28 +855,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         staged_nt = nt;
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
       }
+      if (stats && (n != stat_n || nt != stat_nt)) {
+        if (stat_n >= 0) flush_stats(stat_n, stat_nt);
+        stat_n = n;
+        stat_nt = nt;
+      }
       const int buf = k_local & 1;
-      mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
-      tc_fence_after();
       const uint32_t acc_addr = tmem_base + buf * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
       const int row = quarter * 32 + lane;
       const int t = t0 + row;
       const bool t_ok = t < d.t_out;
-      const int n_chunks32 = g.n_tile / 32;
-      const bool tail16 = (g.n_tile & 31) != 0;
-      for (int ch = 0; ch < n_chunks32; ++ch) {
+      const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
+      bool released = false;  // this thread's ACC_EMPTY arrival (exactly one per tile)
+      bool waited = false;
+      for (int ch = half, ci = 0; ch < n_chunks32; ch += 2, ++ci) {
         if (d.reserved_ & 16) break;
-        float v[32];
-        tmem_ld32(acc_addr + ch * 32, v);
-        if (ch == n_chunks32 - 1 && !tail16) {  // last TMEM read: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(ACC_EMPTY(buf));
-        }
         const int co0 = nt * g.n_tile + ch * 32;
-        float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
-        if (d.skip_mode == VQVS_SKIP_IDENTITY && t_ok) {
-          // all 32 skip loads first (they cannot be hoisted over the stores below by the compiler)
-          float sk[32];
+        // identity-skip operands are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs)
+        float sk[32];
+        if (skip_id && t_ok) {
           const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
                                         : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
           if (d.skip_resize == VQVS_RESIZE_NONE) {
@@ -777,12 +889,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               sk[j] = 0.5f * (p.x + p.y);
             }
           }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += sk[j];
+          for (int j = 0; j < 32; ++j) sk[j] = 0.f;
         }
+        if (!waited) {
+          PROF_ADD(1, tprev);
+          mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
+          tc_fence_after();
+          PROF_ADD(0, tprev);
+          waited = true;
+        }
+        float v[32];
+        tmem_ld32(acc_addr + ch * 32, v);
+        if (ch + 2 >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY(buf));
+          released = true;
+        }
+        float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float o = v[j] + s_bias[ch * 32 + j];
+          float o = v[j] + sk[j] + s_bias[ch * 32 + j];
           if (t_ok) {
             if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
           } else {
@@ -790,29 +918,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           }
           v[j] = o;
         }
-        if (d.stats_out && !(d.reserved_ & 1)) {
-          float sq[32];
+        if (stats) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float s2 = column_sums32(sq, lane);
+          for (int j = 0; j < 32; ++j) sk[j] = v[j] * v[j];
+          const float s2 = column_sums32(sk, lane);
           const float s1 = column_sums32(v, lane);
-          atomicAdd(s_stat + ch * 32 + lane, s1);  // combine the four row quarters in shared memory
-          atomicAdd(s_stat + 256 + ch * 32 + lane, s2);
+          rs1[ci & 3] += (double)s1;  // lane l <-> channel co0 + l
+          rs2[ci & 3] += (double)s2;
         }
       }
-      if (tail16 || (d.reserved_ & 16) || n_chunks32 == 0) {
+      if (!released) {
+        if (!waited) {
+          PROF_ADD(1, tprev);
+          mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
+          tc_fence_after();
+          PROF_ADD(0, tprev);
+        }
         float v[16];
         const int cbase = n_chunks32 * 32;
-        if (tail16) tmem_ld16(acc_addr + cbase, v);
+        const bool do_tail = tail16 && half == 0;
+        if (do_tail) tmem_ld16(acc_addr + cbase, v);
         tc_fence_before();
         mbar_arrive(ACC_EMPTY(buf));
-        if (tail16 && !(d.reserved_ & 16)) {
+        if (do_tail && !(d.reserved_ & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = nt * g.n_tile + cbase + j;
             float o = v[j] + s_bias[cbase + j];
             if (t_ok) {
-              if (d.skip_mode == VQVS_SKIP_IDENTITY) {
+              if (skip_id) {
                 const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
                                              : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
                 if (d.skip_resize == VQVS_RESIZE_NONE) o += __ldg(sp + t);
@@ -823,28 +957,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             } else {
               o = 0.f;
             }
-            if (d.stats_out) {
+            if (stats) {  // tiny configurations only: straight to global
               const float s1 = warp_sum(o), s2 = warp_sum(o * o);
               if (lane == 0) {
-                atomicAdd(s_stat + cbase + j, s1);
-                atomicAdd(s_stat + 256 + cbase + j, s2);
+                double* st = d.stats_out + ((size_t)n * d.c_out + co) * 2;
+                atomicAdd(st, (double)s1);
+                atomicAdd(st + 1, (double)s2);
               }
             }
           }
         }
       }
-      if (d.stats_out && !(d.reserved_ & 1)) {
-        // one fp64 atomic per (channel, statistic) and tile
-        asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-        for (int i = etid; i < 2 * g.n_tile; i += EPI_WARPS * 32) {
-          const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
-          const float val = s_stat[which * 256 + c];
-          s_stat[which * 256 + c] = 0.f;
-          atomicAdd(d.stats_out + ((size_t)n * d.c_out + nt * g.n_tile + c) * 2 + which, (double)val);
-        }
-        asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-      }
     }
+    if (stats && stat_n >= 0) flush_stats(stat_n, stat_nt);
+    if (prof) for (int i = 0; i < 4; ++i) g_prof[12 + i] = acc_[i];
     tc_fence_before();
   }
   __syncthreads();
@@ -1131,6 +1257,15 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   grid = ceil_div(g.tiles_total, g.tiles_per_cta);
   umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_debug_prof(unsigned long long* host32) {
+  cudaError_t e = cudaMemcpyFromSymbol(host32, umma::g_prof, 32 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    set_error("vqvs_debug_prof: %s", cudaGetErrorString(e));
+    return VQVS_ECUDA;
+  }
   return VQVS_OK;
 }
 
