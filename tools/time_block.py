@@ -23,5 +23,5 @@ print(" ".join("%s=%.3fms" % ({2: "umma", 1: "simt", 3: "gn"}[k], ms) for (k, _)
 if int(os.environ.get("VQVS_DEBUG_FLAGS", "0")) & 512:
     buf = (C.c_uint64 * 32)()
     L.check(L.load().vqvs_debug_prof(buf))
-    names = ["xf.wait_ab", "xf.wait_raw", "xf.work", "xf.loop", "tma.wait_empty", "tma.issue", "tma.-", "tma.-", "mma.wait_a", "mma.issue", "mma.wait_acc", "mma.loop", "epi.wait_full", "epi.work", "epi.-", "epi.-"]
+    names = ["xf.wait_ab", "xf.wait_raw", "xf.work", "xf.loop", "tma.wait_empty", "tma.issue", "tma.-", "tma.-", "mma.wait_a", "mma.issue", "mma.wait_acc", "mma.loop", "epi.wait_full", "epi.stats+next", "epi.tmem_ld", "epi.store"]
     print(" | ".join("%s=%d" % (n, buf[i]) for i, n in enumerate(names) if buf[i]))

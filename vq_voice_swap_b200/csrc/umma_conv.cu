@@ -36,7 +36,8 @@ constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
 constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
 constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
 constexpr int EPI_WARP0 = 12;     // warps 12..19 <-> TMEM lane quarters (warp & 3)
-constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
+constexpr int EPI_WARPS = 4;      // two warps per lane quarter split the column chunks
+constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
 constexpr int MAX_RAW_SLOTS = 16;
@@ -399,13 +400,13 @@ struct StageView {
 
 // Row-wise item: the same (8-channel chunk, row) of NK consecutive K blocks -> bf16 hi/lo operand rows.
 // raw / a / ss point at the first K block; the others follow at raw_kb / a_kb bytes and 16 channels.
-template <int NK>
+template <int NK, bool DOWN>
 __device__ __forceinline__ void transform_rowwise(const StageView& v, const uint8_t* raw0, int raw_kb, uint8_t* a0, int a_kb,
                                                   const float2* ss0, int chunk, int row) {
   const int tc = v.tcs + row;
   float x[NK][8];
   if (tc >= 0 && tc < v.t_conv) {
-    if (v.resize != VQVS_RESIZE_DOWN2) {
+    if (!DOWN) {
       const int o = (chunk * 8) * v.box_w + (tc - v.x0);
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
@@ -498,8 +499,15 @@ __device__ __forceinline__ bool elect_one() {
 
 // Optional role profiler (debug flag 512): cycles per phase of block 0, read back with vqvs_debug_prof.
 __device__ unsigned long long g_prof[32];
-#define PROF_T0() const long long p0_ = prof ? clock64() : 0
+#ifdef VQVS_PROF
 #define PROF_ADD(slot, since) do { if (prof) { const long long now_ = clock64(); acc_[slot] += now_ - (since); (since) = now_; } } while (0)
+#define PROF_DECL(cond) const bool prof = (cond); long long acc_[4] = {0, 0, 0, 0}; long long tprev = prof ? clock64() : 0
+#define PROF_STORE(base) do { if (prof) for (int i_ = 0; i_ < 4; ++i_) g_prof[(base) + i_] = acc_[i_]; } while (0)
+#else
+#define PROF_ADD(slot, since) do { } while (0)
+#define PROF_DECL(cond) do { } while (0)
+#define PROF_STORE(base) do { } while (0)
+#endif
 
 struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division on the critical path
   int idx, n;
@@ -581,9 +589,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
-    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && threadIdx.x == 0;
-    long long acc_[4] = {0, 0, 0, 0};
-    long long tprev = prof ? clock64() : 0;
+    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && threadIdx.x == 0);
     // this thread's fixed item of a row-wise stage
     const int my_chunk = threadIdx.x >> 7, my_row = threadIdx.x & (TILE_M - 1);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
@@ -621,7 +627,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
           PROF_ADD(1, tprev);
-          const StageView& v = is_skip ? vs : vm;
+          StageView v = vm;  // by value: keeps the views in registers
+          if (is_skip) v = vs;
           const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes;
           const float2* ss = s_ss + kb0 * KBLK;
           if (d.reserved_ & 64) {
@@ -635,16 +642,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             }
           } else {
             // warps 0..7: the 128 main rows of both chunks (all K blocks of the stage); last warp: the halo rows
+            const bool down = v.resize == VQVS_RESIZE_DOWN2;
             if (warp < XFORM_WARPS - 1) {
-              if (nk == 2) transform_rowwise<2>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
-              else transform_rowwise<1>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
+              if (nk == 2 && !down) {
+                transform_rowwise<2, false>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
+              } else {
+                for (int k = 0; k < nk; ++k) {
+                  if (down) transform_rowwise<1, true>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
+                  else transform_rowwise<1, false>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
+                }
+              }
             } else {
               const int n_extra = v.n_rows - TILE_M;
-              for (int i = lane; i < 2 * n_extra; i += 32) {
-                const int chunk = i >= n_extra;
-                const int row = TILE_M + (chunk ? i - n_extra : i);
-                if (nk == 2) transform_rowwise<2>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, chunk, row);
-                else transform_rowwise<1>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, chunk, row);
+              for (int i = lane; i < nk * 2 * n_extra; i += 32) {
+                const int q = i / n_extra;  // (k block, chunk)
+                const int row = TILE_M + (i - q * n_extra);
+                const int k = q >> 1;
+                if (down) transform_rowwise<1, true>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, q & 1, row);
+                else transform_rowwise<1, false>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, q & 1, row);
               }
             }
           }
@@ -671,7 +686,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         PROF_ADD(2, tprev);
       }
     }
-    if (prof) for (int i = 0; i < 4; ++i) g_prof[i] = acc_[i];
+    PROF_STORE(0);
   } else if (warp == TMA_RAW_WARP) {
     // =========================== TMA: raw activation boxes (warp-uniform loop, elected issue) ==========
     if (g.tma) {
@@ -765,9 +780,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const uint32_t a_kb16 = g.a_kb_bytes >> 4;
     if (g.w_resident) mbar_wait(W_FULL, 0);
     Ring ab(g.ab_slots);
-    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && lane == 0;
-    long long acc_[4] = {0, 0, 0, 0};
-    long long tprev = prof ? clock64() : 0;
+    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && lane == 0);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
       const int buf = k_local & 1;
       PROF_ADD(3, tprev);
@@ -814,7 +827,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         ab.next();
       }
     }
-    if (prof) for (int i = 0; i < 4; ++i) g_prof[8 + i] = acc_[i];
+    PROF_STORE(8);
   } else {
     // =========================== epilogue warps ===========================
     const int quarter = warp & 3;              // TMEM lanes [32*quarter, +32) belong to this warp
@@ -822,17 +835,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const int etid = threadIdx.x - EPI_WARP0 * 32;
     int staged_nt = -1, stat_n = -1, stat_nt = 0;
     // running per-channel (sum, sumsq) of this warp's rows for up to 4 chunks, flushed when the sample changes
-    double rs1[4] = {0, 0, 0, 0}, rs2[4] = {0, 0, 0, 0};
-    const bool prof = (d.reserved_ & 512) && blockIdx.x == 0 && etid == 0;
-    long long acc_[4] = {0, 0, 0, 0};
-    long long tprev = prof ? clock64() : 0;
+    double rs1[2] = {0, 0}, rs2[2] = {0, 0};
+    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && etid == 0);
     const int n_chunks32 = g.n_tile / 32;
     const bool tail16 = (g.n_tile & 31) != 0;
     const bool stats = d.stats_out && !(d.reserved_ & 1);
     auto flush_stats = [&](int fn, int fnt) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ch = half + 2 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int ch = half + EPI_SPLIT * i;
         if (ch < n_chunks32) {
           double* st = d.stats_out + ((size_t)fn * d.c_out + fnt * g.n_tile + ch * 32 + lane) * 2;
           atomicAdd(st, rs1[i]);
@@ -868,8 +879,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
       bool released = false;  // this thread's ACC_EMPTY arrival (exactly one per tile)
       bool waited = false;
-      for (int ch = half, ci = 0; ch < n_chunks32; ch += 2, ++ci) {
-        if (d.reserved_ & 16) break;
+#pragma unroll 1
+      for (int ci = 0; ci < 8 / EPI_SPLIT; ++ci) {
+        const int ch = half + EPI_SPLIT * ci;
+        if (ch >= n_chunks32 || (d.reserved_ & 16)) break;
         const int co0 = nt * g.n_tile + ch * 32;
         // identity-skip operands are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs)
         float sk[32];
@@ -889,9 +902,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               sk[j] = 0.5f * (p.x + p.y);
             }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sk[j] = 0.f;
         }
         if (!waited) {
           PROF_ADD(1, tprev);
@@ -902,29 +912,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
         float v[32];
         tmem_ld32(acc_addr + ch * 32, v);
-        if (ch + 2 >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
+        PROF_ADD(2, tprev);
+        if (ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
           tc_fence_before();
           mbar_arrive(ACC_EMPTY(buf));
           released = true;
         }
         float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
+        const float* bias = s_bias + ch * 32;
+        if (t_ok) {
+          if (skip_id) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float o = v[j] + sk[j] + s_bias[ch * 32 + j];
-          if (t_ok) {
-            if (!(d.reserved_ & 2)) outp[(size_t)j * d.t_out] = o;
-          } else {
-            o = 0.f;
+            for (int j = 0; j < 32; ++j) v[j] += sk[j];
           }
-          v[j] = o;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] += bias[j];
+            *outp = v[j];
+            outp += d.t_out;
+          }
+        } else {  // rows beyond the sequence end (last tile only): no store, no statistics
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
+        PROF_ADD(3, tprev);
         if (stats) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) sk[j] = v[j] * v[j];
           const float s2 = column_sums32(sk, lane);
           const float s1 = column_sums32(v, lane);
-          rs1[ci & 3] += (double)s1;  // lane l <-> channel co0 + l
-          rs2[ci & 3] += (double)s2;
+          // lane l <-> channel co0 + l; static indices keep the accumulators in registers
+          if (ci == 0) { rs1[0] += (double)s1; rs2[0] += (double)s2; }
+          else if (ci == 1) { rs1[1] += (double)s1; rs2[1] += (double)s2; }
+          else {  // wide N tiles (deep, short layers): straight to global
+            double* st = d.stats_out + ((size_t)n * d.c_out + co0 + lane) * 2;
+            atomicAdd(st, (double)s1);
+            atomicAdd(st + 1, (double)s2);
+          }
         }
       }
       if (!released) {
@@ -970,7 +994,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     }
     if (stats && stat_n >= 0) flush_stats(stat_n, stat_nt);
-    if (prof) for (int i = 0; i < 4; ++i) g_prof[12 + i] = acc_[i];
+    PROF_STORE(12);
     tc_fence_before();
   }
   __syncthreads();
