@@ -36,7 +36,7 @@ constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
 constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
 constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
 constexpr int EPI_WARP0 = 12;     // warps 12..19 <-> TMEM lane quarters (warp & 3)
-constexpr int EPI_WARPS = 4;      // two warps per lane quarter split the column chunks
+constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
@@ -583,8 +583,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const uint32_t tmem_base = *tmem_holder;
   const int total_stages = g.main_stages + g.skip_stages;
 
+#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
+#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 136;")
   if (warp < XFORM_WARPS) {
     // =========================== operand producers (transform warps) ===========================
+    REG_DEC();
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
@@ -689,6 +692,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     PROF_STORE(0);
   } else if (warp == TMA_RAW_WARP) {
     // =========================== TMA: raw activation boxes (warp-uniform loop, elected issue) ==========
+    REG_DEC();
     if (g.tma) {
       Ring rw(g.raw_slots);
       const uint32_t raw_base = smem_u32(smem + g.off_raw);
@@ -735,6 +739,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == TMA_W_WARP) {
     // =========================== TMA: weight image ===========================
+    REG_DEC();
     if (g.w_resident) {  // loaded once, reused by every tile of this CTA
       if (elect_one()) {
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed);
@@ -770,6 +775,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (warp-uniform loop, elected issue) ===========================
+    REG_DEC();
     const uint32_t idesc = make_idesc(g.n_tile);
     // descriptor = constant fields + (address >> 4); the address field never carries into LBO
     const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
@@ -830,6 +836,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     PROF_STORE(8);
   } else {
     // =========================== epilogue warps ===========================
+    REG_INC();
     const int quarter = warp & 3;              // TMEM lanes [32*quarter, +32) belong to this warp
     const int half = (warp - EPI_WARP0) >> 2;  // the two warps of a quarter take alternate 32-column chunks
     const int etid = threadIdx.x - EPI_WARP0 * 32;
