@@ -585,9 +585,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 
 #define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
 #define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 136;")
+  if (warp < EPI_WARP0) {
+  REG_DEC();  // one instruction for all three non-epilogue warpgroups (setmaxnreg is warpgroup-collective)
   if (warp < XFORM_WARPS) {
     // =========================== operand producers (transform warps) ===========================
-    REG_DEC();
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
@@ -692,7 +693,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     PROF_STORE(0);
   } else if (warp == TMA_RAW_WARP) {
     // =========================== TMA: raw activation boxes (warp-uniform loop, elected issue) ==========
-    REG_DEC();
     if (g.tma) {
       Ring rw(g.raw_slots);
       const uint32_t raw_base = smem_u32(smem + g.off_raw);
@@ -739,7 +739,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == TMA_W_WARP) {
     // =========================== TMA: weight image ===========================
-    REG_DEC();
     if (g.w_resident) {  // loaded once, reused by every tile of this CTA
       if (elect_one()) {
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed);
@@ -775,7 +774,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (warp-uniform loop, elected issue) ===========================
-    REG_DEC();
     const uint32_t idesc = make_idesc(g.n_tile);
     // descriptor = constant fields + (address >> 4); the address field never carries into LBO
     const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
@@ -834,6 +832,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     }
     PROF_STORE(8);
+  }
   } else {
     // =========================== epilogue warps ===========================
     REG_INC();
