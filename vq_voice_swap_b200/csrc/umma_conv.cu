@@ -1285,8 +1285,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   g.tiles_t = ceil_div(d->t_out, umma::TILE_M);
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
-  g.tiles_per_cta = ceil_div(g.tiles_total, grid);
-  grid = ceil_div(g.tiles_total, g.tiles_per_cta);
+  g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
   umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
