@@ -36,7 +36,7 @@ constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
 constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
 constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
 constexpr int EPI_WARP0 = 12;     // warps 12..19 <-> TMEM lane quarters (warp & 3)
-constexpr int EPI_WARPS = 4;      // two warps per lane quarter split the column chunks
+constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
@@ -583,10 +583,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const uint32_t tmem_base = *tmem_holder;
   const int total_stages = g.main_stages + g.skip_stages;
 
-// NOTE: per-role register budgets via setmaxnreg (72 / 136 with 8 epilogue warps) compiled spill-free but
-// deadlocked whole-network runs on the B200 (single ResBlocks passed); left disabled until understood.
-#define REG_DEC() do { } while (0)
-#define REG_INC() do { } while (0)
+// Per-role register budgets.  setmaxnreg moves registers inside the CTA's OWN pool (threads x launch
+// registers = 640 x 96 = 61440), so 12 warps x 72 + 8 warps x 128 = 1888 <= 20 x 96 = 1920 per lane must hold
+// (72 / 136 overdraws the pool and the last epilogue warpgroup spins in USETMAXREG.TRY_ALLOC forever).
+#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
+#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 128;")
   if (warp < EPI_WARP0) {
   REG_DEC();  // one instruction for all three non-epilogue warpgroups (setmaxnreg is warpgroup-collective)
   if (warp < XFORM_WARPS) {
