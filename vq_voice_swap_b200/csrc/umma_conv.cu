@@ -31,14 +31,16 @@ namespace umma {
 constexpr int TILE_M = 128;
 constexpr int KBLK = 16;  // channels per MMA K block (kind::f16: K = 16)
 // warp roles of the persistent CTA (one CTA per SM)
+// (epilogue first: low warp ids; warpgroups 0-1 = epilogue, 2-4 = MMA / TMA / transform)
+constexpr int EPI_WARP0 = 0;      // warps 0..7 <-> TMEM lane quarters (warp & 3)
+constexpr int MMA_WARP = 8;       // single-thread tcgen05.mma issue
+constexpr int TMA_W_WARP = 9;     // weight image (resident or streamed per K block)
+constexpr int TMA_RAW_WARP = 10;  // raw fp32 activation boxes -> staging ring
+constexpr int XFORM_WARP0 = 11;   // warps 11..19 transform
 constexpr int XFORM_WARPS = 9;    // 8 warps transform the 128 main rows x 2 chunks, the 9th the halo rows
-constexpr int TMA_RAW_WARP = 9;   // raw fp32 activation boxes -> staging ring
-constexpr int TMA_W_WARP = 10;    // weight image (resident or streamed per K block)
-constexpr int MMA_WARP = 11;      // single-thread tcgen05.mma issue
-constexpr int EPI_WARP0 = 12;     // warps 12..19 <-> TMEM lane quarters (warp & 3)
 constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
-constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int THREADS = (XFORM_WARP0 + XFORM_WARPS) * 32;
 constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
 constexpr int MAX_RAW_SLOTS = 16;
 constexpr int MAX_AB_SLOTS = 8;
@@ -55,9 +57,6 @@ struct Geo {
   long long per_tile_bytes; // packed weight image bytes per N tile
   // shared-memory plan (byte offsets from the dynamic smem base)
   int off_stat, off_ss, off_bias, off_w, off_raw, off_ab;
-  // TMA-store epilogue: the output tile is staged channel-major [epi_ch][128] fp32 (two buffers) and
-  // leaves through cp.async.bulk.tensor; the statistics are reduced from the staged copy
-  int epi_tma, epi_ch, off_stage, off_acc;
   int kbs;                        // K blocks per pipeline stage (2 when the rings still fit, else 1)
   int raw_kb_bytes;               // raw staging bytes of ONE K block (a slot holds kbs of them)
   int raw_slot_bytes, raw_slots;  // fp32 staging ring filled by TMA (0 slots in direct mode)
@@ -76,8 +75,7 @@ struct Geo {
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, bool out_tma,
-                     Geo* g) {
+static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
   g->n_tiles = (c_out + 255) / 256;
   if (c_out % g->n_tiles) return false;
@@ -125,13 +123,7 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->off_stat = off;
   g->off_ss = off;   off += c_in * 8;
   g->off_bias = off; off += g->n_tile * 4;
-  off = align_up(off, 16);
-  g->off_acc = off;  off += 2 * g->n_tile * 8;  // fp64 running (sum, sumsq) per channel of the N tile
   off = align_up(off, 128);
-  g->epi_tma = (out_tma && (g->n_tile == 32 || g->n_tile == 64 || g->n_tile == 128 || g->n_tile == 256)) ? 1 : 0;
-  g->epi_ch = g->n_tile < 64 ? g->n_tile : 64;
-  g->off_stage = off;
-  if (g->epi_tma) off += 2 * g->epi_ch * TILE_M * 4;
   g->off_w = off;
   const long long w_img = g->per_tile_bytes;
   g->w_resident = (g->n_tiles == 1 && w_img <= 100 * 1024) ? 1 : 0;
@@ -139,12 +131,12 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->off_raw = off;
   const int left0 = budget - off;
   bool ok = false;
-  for (int kbs = 4; kbs >= 1 && !ok; kbs /= 2) {
+  for (int kbs = 2; kbs >= 1 && !ok; --kbs) {
     const int ab_slot = kbs * (g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
     const int raw_slot = kbs * g->raw_kb_bytes;
     const int min_ab = 2, min_raw = tma ? 3 : 0;
     if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
-    if (kbs >= 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
+    if (kbs == 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
     int ab = MAX_AB_SLOTS;
     while (ab > min_ab && left0 - ab * ab_slot < (tma ? 4 * raw_slot : 0)) --ab;
     if (left0 - ab * ab_slot < min_raw * raw_slot) continue;
@@ -519,19 +511,6 @@ __device__ unsigned long long g_prof[32];
 #define PROF_STORE(base) do { } while (0)
 #endif
 
-// TMA tensor store of one [rows x 128 positions] fp32 box from shared memory (SASS: UTMASTG); positions
-// beyond the end of the sequence are clipped by the hardware.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(src), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division on the critical path
   int idx, n;
   uint32_t ph;
@@ -546,8 +525,8 @@ struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
-                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb,
-                 const __grid_constant__ CUtensorMap tm_out, const VqvsConv d, const Geo g) {
+                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
+                 const Geo g) {
   extern __shared__ __align__(128) uint8_t smem[];
   // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
@@ -600,8 +579,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       if (d.s_b) tma_prefetch_desc(&tm_sb);
     }
   }
-  if (warp == EPI_WARP0 && lane == 0 && g.epi_tma) tma_prefetch_desc(&tm_out);
-  for (int i = threadIdx.x; i < 2 * g.n_tile; i += THREADS) reinterpret_cast<double*>(smem + g.off_acc)[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -613,24 +590,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 // (72 / 136 overdraws the pool and the last epilogue warpgroup spins in USETMAXREG.TRY_ALLOC forever).
 #define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
 #define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 128;")
-  if (warp < EPI_WARP0) {
+  if (warp >= EPI_WARP0 + EPI_WARPS) {
   REG_DEC();  // one instruction for all three non-epilogue warpgroups (setmaxnreg is warpgroup-collective)
-  if (warp < XFORM_WARPS) {
+  if (warp >= XFORM_WARP0) {
+    const int xtid = threadIdx.x - XFORM_WARP0 * 32, xwarp = warp - XFORM_WARP0;
     // =========================== operand producers (transform warps) ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
-    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && threadIdx.x == 0);
+    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && xtid == 0);
     // this thread's fixed item of a row-wise stage
-    const int my_chunk = threadIdx.x >> 7, my_row = threadIdx.x & (TILE_M - 1);
+    const int my_chunk = xtid >> 7, my_row = xtid & (TILE_M - 1);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
       const int tile = tile_first + k_local * tile_stride;
       TILE_COORDS(tile)
       (void)nt;
       if (d.act && n != staged_n) {  // per-sample GroupNorm/FiLM affine
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
-        for (int i = threadIdx.x; i < c_in; i += XFORM_WARPS * 32)
+        for (int i = xtid; i < c_in; i += XFORM_WARPS * 32)
           s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
         staged_n = n;
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
@@ -668,21 +646,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           } else if (v.resize == VQVS_RESIZE_UP2) {
             const int first = v.tcs >> 1;
             const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
-            for (int i = threadIdx.x; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
+            for (int i = xtid; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
               const int q = i / nsrc, j = i - q * nsrc;  // q = (k block, chunk)
               transform_up2(v, raw + (q >> 1) * g.raw_kb_bytes, a_slot + (q >> 1) * g.a_kb_bytes, ss + (q >> 1) * KBLK, q & 1, first + j);
             }
           } else {
             // warps 0..7: the 128 main rows of both chunks (all K blocks of the stage); last warp: the halo rows
             const bool down = v.resize == VQVS_RESIZE_DOWN2;
-            if (warp < XFORM_WARPS - 1) {
-              if (!down) {
-                int k = 0;
-                for (; k + 2 <= nk; k += 2)
-                  transform_rowwise<2, false>(v, raw + k * g.raw_kb_bytes, g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, g.a_kb_bytes,
-                                              ss + k * KBLK, my_chunk, my_row);
-                if (k < nk)
-                  transform_rowwise<1, false>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
+            if (xwarp < XFORM_WARPS - 1) {
+              if (nk == 2 && !down) {
+                transform_rowwise<2, false>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
               } else {
                 for (int k = 0; k < nk; ++k) {
                   if (down) transform_rowwise<1, true>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
@@ -705,7 +678,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const bool act = !is_skip && d.act;
           const int pad = is_skip ? 0 : g.pad;
           const int n_rows = TILE_M + 2 * pad;
-          for (int i = threadIdx.x; i < nk * 2 * n_rows; i += XFORM_WARPS * 32) {
+          for (int i = xtid; i < nk * 2 * n_rows; i += XFORM_WARPS * 32) {
             const int q = i / n_rows, row = i - q * n_rows;
             const int c8 = kb0 * KBLK + q * 8;
             uint8_t* a_hi = a_slot + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
@@ -873,7 +846,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const int half = (warp - EPI_WARP0) >> 2;  // the two warps of a quarter take alternate 32-column chunks
     const int etid = threadIdx.x - EPI_WARP0 * 32;
     int staged_nt = -1, stat_n = -1, stat_nt = 0;
-    uint32_t epi_cnt = 0;
     // running per-channel (sum, sumsq) of this warp's rows for up to 4 chunks, flushed when the sample changes
     double rs1[2] = {0, 0}, rs2[2] = {0, 0};
     PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && etid == 0);
@@ -906,7 +878,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         staged_nt = nt;
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
       }
-      if (!g.epi_tma && stats && (n != stat_n || nt != stat_nt)) {
+      if (stats && (n != stat_n || nt != stat_nt)) {
         if (stat_n >= 0) flush_stats(stat_n, stat_nt);
         stat_n = n;
         stat_nt = nt;
@@ -917,110 +889,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       const int t = t0 + row;
       const bool t_ok = t < d.t_out;
       const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
-      if (g.epi_tma) {
-        // ---------------- staged epilogue: TMEM -> registers -> smem [channel][128] -> TMA store ----------------
-        double* s_acc = reinterpret_cast<double*>(smem + g.off_acc);  // [2][n_tile] running (sum, sumsq), one owner lane each
-        if (stats && (n != stat_n || nt != stat_nt)) {                // flush when the CTA moves to another sample / N tile
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-          if (stat_n >= 0)
-            for (int i = etid; i < 2 * g.n_tile; i += EPI_WARPS * 32) {
-              const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
-              atomicAdd(d.stats_out + ((size_t)stat_n * d.c_out + stat_nt * g.n_tile + c) * 2 + which, s_acc[i]);
-              s_acc[i] = 0.0;
-            }
-          stat_n = n;
-          stat_nt = nt;
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-        }
-        const int n_sub = g.n_tile / g.epi_ch;          // staging chunks of epi_ch channels
-        const int sub32 = g.epi_ch / 32;                // 32-column groups per staging chunk (1 or 2)
-        bool waited = false;
-        for (int sc = 0; sc < n_sub; ++sc) {
-          float* sbuf = reinterpret_cast<float*>(smem + g.off_stage) + (epi_cnt & 1) * (g.epi_ch * TILE_M);
-          ++epi_cnt;
-          const bool mine = half < sub32;               // this warp owns columns [sc*epi_ch + half*32, +32)
-          const int col0 = sc * g.epi_ch + half * 32;
-          const int co0 = nt * g.n_tile + col0;
-          float sk[32];
-          if (mine && skip_id && t_ok) {                // identity-skip operands, fetched before the accumulator wait
-            const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
-                                          : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
-            if (d.skip_resize == VQVS_RESIZE_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + t);
-            } else if (d.skip_resize == VQVS_RESIZE_UP2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sk[j] = __ldg(sp + (size_t)j * d.t_skip + (t >> 1));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)j * d.t_skip + 2 * t));
-                sk[j] = 0.5f * (p.x + p.y);
-              }
-            }
-          }
-          if (!waited) {
-            mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
-            tc_fence_after();
-            waited = true;
-          }
-          // the TMA store that used this staging buffer two chunks ago must have finished reading it
-          if (etid == 0) tma_store_wait_read<1>();
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-          if (mine) {
-            float v[32];
-            tmem_ld32(acc_addr + col0, v);
-            if (sc == n_sub - 1) {  // last TMEM read of this tile by this warp
-              tc_fence_before();
-              mbar_arrive(ACC_EMPTY(buf));
-            }
-            const float* bias = s_bias + col0;
-            float* dst = sbuf + (half * 32) * TILE_M + row;
-            if (t_ok) {
-              if (skip_id) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += sk[j];
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j * TILE_M] = v[j] + bias[j];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j * TILE_M] = 0.f;  // keeps the statistics exact; the store clips these rows
-            }
-            fence_proxy_async();
-          } else if (sc == n_sub - 1) {
-            tc_fence_before();
-            mbar_arrive(ACC_EMPTY(buf));
-          }
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-          if (etid == 0) {
-            tma_store_2d(&tm_out, smem_u32(sbuf), t0, n * d.c_out + nt * g.n_tile + sc * g.epi_ch);
-            tma_store_commit();
-          }
-          if (stats) {
-            // half a warp per channel: 16 lanes x 2 float4 cover the 128 positions, conflict-free
-            const int per_warp = g.epi_ch / EPI_WARPS;  // 8 (epi_ch 64) or 4 (epi_ch 32)
-            const int wl = warp - EPI_WARP0;
-            for (int i = 0; i < per_warp; i += 2) {
-              const int c = wl * per_warp + i + (lane >> 4);
-              const float4* rowp = reinterpret_cast<const float4*>(sbuf + c * TILE_M);
-              const float4 a = rowp[lane & 15], b = rowp[16 + (lane & 15)];
-              float s1 = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
-              float s2 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-#pragma unroll
-              for (int o = 8; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              }
-              if ((lane & 15) == 0) {  // sole owner of channel (sc, c): plain read-modify-write
-                s_acc[sc * g.epi_ch + c] += (double)s1;
-                s_acc[g.n_tile + sc * g.epi_ch + c] += (double)s2;
-              }
-            }
-          }
-        }
-        continue;
-      }
       bool released = false;  // this thread's ACC_EMPTY arrival (exactly one per tile)
       bool waited = false;
 #pragma unroll 1
@@ -1137,19 +1005,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
       }
     }
-    if (g.epi_tma) {
-      if (stats && stat_n >= 0) {
-        double* s_acc = reinterpret_cast<double*>(smem + g.off_acc);
-        asm volatile("bar.sync 3, %0;" ::"n"(EPI_WARPS * 32));
-        for (int i = etid; i < 2 * g.n_tile; i += EPI_WARPS * 32) {
-          const int which = i >= g.n_tile, c = which ? i - g.n_tile : i;
-          atomicAdd(d.stats_out + ((size_t)stat_n * d.c_out + stat_nt * g.n_tile + c) * 2 + which, s_acc[i]);
-        }
-      }
-      if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output tiles have landed
-    } else if (stats && stat_n >= 0) {
-      flush_stats(stat_n, stat_nt);
-    }
+    if (stats && stat_n >= 0) flush_stats(stat_n, stat_nt);
     PROF_STORE(12);
     tc_fence_before();
   }
@@ -1308,12 +1164,8 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
   if (c_skip && (d->s_a % umma::KBLK || d->s_b % umma::KBLK)) return 0;
   if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // paired loads need even rows
   const bool tma = tma_eligible(d);
-  const bool out_tma = d->t_out % 4 == 0 && aligned16(d->out);
-  const int c_in = d->c_a + d->c_b;
-  for (int in_mode = tma ? 1 : 0; in_mode >= 0; --in_mode)
-    for (int out_mode = out_tma ? 1 : 0; out_mode >= 0; --out_mode)
-      if (umma::make_geo(c_in, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, in_mode != 0, out_mode != 0, g)) return 1;
-  return 0;
+  if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g)) return 1;
+  return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g) ? 1 : 0;
 }
 
 extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
@@ -1323,7 +1175,7 @@ extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
 
 extern "C" int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip) {
   Geo g;
-  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, false, &g)) return -1;
+  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g)) return -1;
   return (int64_t)g.n_tiles * g.per_tile_bytes;
 }
 
@@ -1331,7 +1183,7 @@ extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c
                                       void* packed, void* stream) {
   Geo g;
   VQVS_CHECK_ARG(w && packed && (c_skip == 0 || w_skip), "pack_conv_weights: null pointer");
-  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, false, &g),
+  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g),
                  "pack_conv_weights: unsupported shape c_out=%d c_in=%d k=%d skip=%d", c_out, c_in, ksize, c_skip);
   umma::pack_weights_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(w, w_skip, c_out, c_in, ksize, c_skip, g, (uint8_t*)packed);
   VQVS_CHECK_LAUNCH("vqvs_pack_conv_weights");
@@ -1370,7 +1222,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // [rows = batch*channels][t] fp32 tensor, boxes of 16 rows x box_w positions, zero fill outside.
-static int encode_map_rows(CUtensorMap* m, const float* base, int rows, int t, int box_w, int box_rows) {
+static int encode_map(CUtensorMap* m, const float* base, int rows, int t, int box_w) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("conv(umma): cuTensorMapEncodeTiled is not available from the driver");
@@ -1378,7 +1230,7 @@ static int encode_map_rows(CUtensorMap* m, const float* base, int rows, int t, i
   }
   const cuuint64_t dims[2] = {(cuuint64_t)t, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)t * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)umma::KBLK};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1388,10 +1240,6 @@ static int encode_map_rows(CUtensorMap* m, const float* base, int rows, int t, i
     return VQVS_ECUDA;
   }
   return VQVS_OK;
-}
-
-static int encode_map(CUtensorMap* m, const float* base, int rows, int t, int box_w) {
-  return encode_map_rows(m, base, rows, t, box_w, umma::KBLK);
 }
 
 extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
@@ -1423,9 +1271,8 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     }
     attr_done = true;
   }
-  alignas(64) CUtensorMap maps[5];
+  alignas(64) CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
-  if (g.epi_tma && (rc = encode_map_rows(&maps[4], d->out, d->batch * d->c_out, d->t_out, umma::TILE_M, g.epi_ch))) return rc;
   if (g.tma) {
     if ((rc = encode_map(&maps[0], d->xa, d->batch * d->c_a, d->t_in, g.main_box_w))) return rc;
     if (d->c_b && (rc = encode_map(&maps[1], d->xb, d->batch * d->c_b, d->t_in, g.main_box_w))) return rc;
@@ -1443,7 +1290,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
-  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], *d, g);
+  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }
