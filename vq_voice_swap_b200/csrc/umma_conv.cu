@@ -58,6 +58,8 @@ struct Geo {
   // shared-memory plan (byte offsets from the dynamic smem base)
   int off_stat, off_ss, off_bias, off_w, off_raw, off_ab;
   int kbs;                        // K blocks per pipeline stage (2 when the rings still fit, else 1)
+  int mt;                         // time tiles per work item: streamed weights are reused by 2 tiles (halves L2->smem traffic)
+  int nbuf;                       // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
   int raw_kb_bytes;               // raw staging bytes of ONE K block (a slot holds kbs of them)
   int raw_slot_bytes, raw_slots;  // fp32 staging ring filled by TMA (0 slots in direct mode)
   int ab_slot_bytes, ab_slots;    // operand ring: kbs A tiles (+ the streamed weights of those K blocks)
@@ -131,9 +133,14 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->off_raw = off;
   const int left0 = budget - off;
   bool ok = false;
-  for (int kbs = 2; kbs >= 1 && !ok; --kbs) {
-    const int ab_slot = kbs * (g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
-    const int raw_slot = kbs * g->raw_kb_bytes;
+  for (int cand = 0; cand < 4 && !ok; ++cand) {
+    // streamed weights: prefer two time tiles per item (mt = 2); resident weights gain nothing from it
+    const int mt = (!g->w_resident && cand < 2) ? 2 : 1;
+    const int kbs = (cand & 1) ? 1 : 2;
+    if (g->w_resident && cand < 2) continue;
+    if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;
+    const int ab_slot = kbs * (mt * g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
+    const int raw_slot = mt * kbs * g->raw_kb_bytes;
     const int min_ab = 2, min_raw = tma ? 3 : 0;
     if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
     if (kbs == 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
@@ -145,6 +152,9 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     if (raw > MAX_RAW_SLOTS) raw = MAX_RAW_SLOTS;
     if (raw > 8) raw = 8;
     g->kbs = kbs;
+    g->mt = mt;
+    g->nbuf = (2 * mt * g->acc_cols <= 512) ? 2 : 1;
+    g->tmem_cols = g->nbuf * mt * g->acc_cols;
     g->ab_slot_bytes = ab_slot;
     g->ab_slots = ab;
     g->raw_slot_bytes = raw_slot;
@@ -551,7 +561,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const int tx_ = (tile) % g.tiles_t;              \
   const int nt = ((tile) / g.tiles_t) % g.n_tiles; \
   const int n = (tile) / (g.tiles_t * g.n_tiles);  \
-  const int t0 = tx_ * TILE_M;
+  const int t0 = tx_ * (TILE_M * g.mt);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RAW_SLOTS; ++i) {
@@ -613,7 +623,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         staged_n = n;
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
       }
-      StageView vm, vs;  // per-tile views of the main taps and of the 1x1 skip
+      StageView vm, vs;  // per-tile views of the main taps and of the 1x1 skip (first tile of the item)
       vm.rows = vs.rows = g.rows;
       vm.box_w = g.main_box_w;  vs.box_w = g.skip_box_w;
       vm.boxes = g.main_boxes;  vs.boxes = 1;
@@ -633,13 +643,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const bool is_skip = st >= g.main_stages;
         const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-        uint8_t* a_slot = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
+        uint8_t* a_slot0 = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
         if (g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
           PROF_ADD(1, tprev);
+         for (int j = 0; j < g.mt; ++j) {  // the time tiles of this item share the weights of the stage
           StageView v = vm;  // by value: keeps the views in registers
           if (is_skip) v = vs;
-          const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes;
+          v.x0 += (j * TILE_M * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2;
+          v.tcs += j * TILE_M;
+          const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes + j * g.kbs * g.raw_kb_bytes;
+          uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
           const float2* ss = s_ss + kb0 * KBLK;
           if (d.reserved_ & 64) {
             // ablation: no staging work at all
@@ -673,7 +687,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               }
             }
           }
+         }
         } else {
+         for (int j = 0; j < g.mt; ++j) {
+          uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
+          const int t0j = t0 + j * TILE_M;
           const Src& src = is_skip ? skip_src : main_src;
           const bool act = !is_skip && d.act;
           const int pad = is_skip ? 0 : g.pad;
@@ -682,8 +700,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             const int q = i / n_rows, row = i - q * n_rows;
             const int c8 = kb0 * KBLK + q * 8;
             uint8_t* a_hi = a_slot + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-            produce_direct(src, n, c8, t0 - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
+            produce_direct(src, n, c8, t0j - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
           }
+         }
         }
         fence_proxy_async();
         __syncwarp();
@@ -717,24 +736,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           if (elect_one()) {
             const uint32_t dst0 = raw_base + rw.idx * g.raw_slot_bytes;
             if (!is_skip) {
-              mbar_expect_tx(RAW_FULL(rw.idx), nk * g.main_boxes * box_bytes);
-              for (int k = 0; k < nk; ++k) {
-                const int c16 = (kb0 + k) * KBLK;
-                const bool from_a = c16 < d.c_a;
-                const CUtensorMap* map = from_a ? &tm_xa : &tm_xb;
-                const int rowc = from_a ? n * d.c_a + c16 : n * d.c_b + (c16 - d.c_a);
-                const uint32_t dst = dst0 + k * g.raw_kb_bytes;
-                tma_box_2d(dst, map, x0m, rowc, RAW_FULL(rw.idx));
-                if (g.main_boxes == 2) tma_box_2d(dst + box_bytes, map, x0m + g.main_box_w, rowc, RAW_FULL(rw.idx));
+              mbar_expect_tx(RAW_FULL(rw.idx), g.mt * nk * g.main_boxes * box_bytes);
+              for (int j = 0; j < g.mt; ++j) {
+                const int xj = x0m + (j * TILE_M * g.main_origin_mul) / 2;
+                for (int k = 0; k < nk; ++k) {
+                  const int c16 = (kb0 + k) * KBLK;
+                  const bool from_a = c16 < d.c_a;
+                  const CUtensorMap* map = from_a ? &tm_xa : &tm_xb;
+                  const int rowc = from_a ? n * d.c_a + c16 : n * d.c_b + (c16 - d.c_a);
+                  const uint32_t dst = dst0 + (j * g.kbs + k) * g.raw_kb_bytes;
+                  tma_box_2d(dst, map, xj, rowc, RAW_FULL(rw.idx));
+                  if (g.main_boxes == 2) tma_box_2d(dst + box_bytes, map, xj + g.main_box_w, rowc, RAW_FULL(rw.idx));
+                }
               }
             } else {
-              mbar_expect_tx(RAW_FULL(rw.idx), nk * KBLK * g.skip_box_w * 4);
-              for (int k = 0; k < nk; ++k) {
-                const int c16 = (kb0 + k) * KBLK;
-                const bool from_a = c16 < d.s_a;
-                const CUtensorMap* map = from_a ? &tm_sa : &tm_sb;
-                const int rowc = from_a ? n * d.s_a + c16 : n * d.s_b + (c16 - d.s_a);
-                tma_box_2d(dst0 + k * g.raw_kb_bytes, map, x0s, rowc, RAW_FULL(rw.idx));
+              mbar_expect_tx(RAW_FULL(rw.idx), g.mt * nk * KBLK * g.skip_box_w * 4);
+              for (int j = 0; j < g.mt; ++j) {
+                const int xj = x0s + (j * TILE_M * g.skip_origin_mul) / 2;
+                for (int k = 0; k < nk; ++k) {
+                  const int c16 = (kb0 + k) * KBLK;
+                  const bool from_a = c16 < d.s_a;
+                  const CUtensorMap* map = from_a ? &tm_sa : &tm_sb;
+                  const int rowc = from_a ? n * d.s_a + c16 : n * d.s_b + (c16 - d.s_a);
+                  tma_box_2d(dst0 + (j * g.kbs + k) * g.raw_kb_bytes, map, xj, rowc, RAW_FULL(rw.idx));
+                }
               }
             }
           }
@@ -757,7 +782,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     } else {
       Ring ab(g.ab_slots);
-      const uint32_t b_base = smem_u32(smem + g.off_ab + g.kbs * g.a_kb_bytes);
+      const uint32_t b_base = smem_u32(smem + g.off_ab + g.mt * g.kbs * g.a_kb_bytes);
       for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
         const int tile = tile_first + k_local * tile_stride;
         const int nt = (tile / g.tiles_t) % g.n_tiles;
@@ -792,12 +817,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     Ring ab(g.ab_slots);
     PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && lane == 0);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-      const int buf = k_local & 1;
+      const int buf = k_local % g.nbuf;
       PROF_ADD(3, tprev);
-      mbar_wait(ACC_EMPTY(buf), ((k_local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      mbar_wait(ACC_EMPTY(buf), ((k_local / g.nbuf) & 1) ^ 1);  // epilogue drained this accumulator set
       tc_fence_after();
       PROF_ADD(2, tprev);
-      const uint32_t d_tmem = tmem_base + buf * g.acc_cols;
+      const uint32_t d_tmem0 = tmem_base + buf * g.mt * g.acc_cols;
       uint32_t acc = 0;
       uint32_t w16 = w_base16;
       for (int st = 0; st < total_stages; ++st) {
@@ -811,21 +836,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
         const uint32_t unit16 = is_skip ? unit_skip16 : unit_main16;
-        const uint32_t b16 = g.w_resident ? w16 : a16 + g.kbs * a_kb16;
+        const uint32_t b16 = g.w_resident ? w16 : a16 + g.mt * g.kbs * a_kb16;
         w16 += nk * unit16;
         const int taps = is_skip ? 1 : d.ksize;
         const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
         if (elect_one()) {
           if (!(d.reserved_ & 4)) {
-            for (int k = 0; k < nk; ++k) {
+            for (int j = 0; j < g.mt; ++j) {
+              const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
+              uint32_t accj = acc;  // 0 only for the first MMA of each accumulator of the item
+              for (int k = 0; k < nk; ++k) {
 #pragma unroll 3
-              for (int tap = 0; tap < taps; ++tap) {
-                const uint64_t da_hi = a_const + (a16 + k * a_kb16 + tap * tap_rows);
-                const uint64_t db_hi = b_const + (b16 + k * unit16 + tap * b_tap_off);
-                mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
-                acc = 1;
-                mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
-                mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+                for (int tap = 0; tap < taps; ++tap) {
+                  const uint64_t da_hi = a_const + (a16 + (j * g.kbs + k) * a_kb16 + tap * tap_rows);
+                  const uint64_t db_hi = b_const + (b16 + k * unit16 + tap * b_tap_off);
+                  mma_bf16(d_tmem, da_hi, db_hi, idesc, accj);
+                  accj = 1;
+                  mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
+                  mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+                }
               }
             }
           }
@@ -883,14 +912,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         stat_n = n;
         stat_nt = nt;
       }
-      const int buf = k_local & 1;
-      const uint32_t acc_addr = tmem_base + buf * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
+      const int buf = k_local % g.nbuf;
+      const uint32_t acc_par = (k_local / g.nbuf) & 1;
       const int row = quarter * 32 + lane;
-      const int t = t0 + row;
-      const bool t_ok = t < d.t_out;
       const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
-      bool released = false;  // this thread's ACC_EMPTY arrival (exactly one per tile)
+      bool released = false;  // this thread's ACC_EMPTY arrival (exactly one per item)
       bool waited = false;
+      uint32_t acc_addr = 0;
+      int t = 0;
+      bool t_ok = false;
+#pragma unroll 1
+     for (int j = 0; j < g.mt; ++j) {  // the time tiles of this item
+      acc_addr = tmem_base + (buf * g.mt + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
+      t = t0 + j * TILE_M + row;
+      t_ok = t < d.t_out;
 #pragma unroll 1
       for (int ci = 0; ci < 8 / EPI_SPLIT; ++ci) {
         const int ch = half + EPI_SPLIT * ci;
@@ -917,7 +952,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
         if (!waited) {
           PROF_ADD(1, tprev);
-          mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
+          mbar_wait(ACC_FULL(buf), acc_par);
           tc_fence_after();
           PROF_ADD(0, tprev);
           waited = true;
@@ -925,7 +960,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         float v[32];
         tmem_ld32(acc_addr + ch * 32, v);
         PROF_ADD(2, tprev);
-        if (ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulator back
+        if (j == g.mt - 1 && ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulators back
           tc_fence_before();
           mbar_arrive(ACC_EMPTY(buf));
           released = true;
@@ -963,10 +998,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           }
         }
       }
+     }  // tiles of the item
       if (!released) {
         if (!waited) {
           PROF_ADD(1, tprev);
-          mbar_wait(ACC_FULL(buf), (k_local >> 1) & 1);
+          mbar_wait(ACC_FULL(buf), acc_par);
           tc_fence_after();
           PROF_ADD(0, tprev);
         }
@@ -1286,7 +1322,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     int cc = 0;
     if (vqvs_device_info(&cc, &sm_count) != VQVS_OK) return VQVS_ECUDA;
   }
-  g.tiles_t = ceil_div(d->t_out, umma::TILE_M);
+  g.tiles_t = ceil_div(d->t_out, umma::TILE_M * g.mt);  // work items along time (mt tiles each)
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
