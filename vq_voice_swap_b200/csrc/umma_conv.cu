@@ -533,6 +533,7 @@ struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division
   }
 };
 
+template <int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
@@ -561,7 +562,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const int tx_ = (tile) % g.tiles_t;              \
   const int nt = ((tile) / g.tiles_t) % g.n_tiles; \
   const int n = (tile) / (g.tiles_t * g.n_tiles);  \
-  const int t0 = tx_ * (TILE_M * g.mt);
+  const int t0 = tx_ * (TILE_M * MT);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RAW_SLOTS; ++i) {
@@ -647,7 +648,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
           PROF_ADD(1, tprev);
-         for (int j = 0; j < g.mt; ++j) {  // the time tiles of this item share the weights of the stage
+         for (int j = 0; j < MT; ++j) {  // the time tiles of this item share the weights of the stage
           StageView v = vm;  // by value: keeps the views in registers
           if (is_skip) v = vs;
           v.x0 += (j * TILE_M * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2;
@@ -689,7 +690,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           }
          }
         } else {
-         for (int j = 0; j < g.mt; ++j) {
+         for (int j = 0; j < MT; ++j) {
           uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
           const int t0j = t0 + j * TILE_M;
           const Src& src = is_skip ? skip_src : main_src;
@@ -736,8 +737,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           if (elect_one()) {
             const uint32_t dst0 = raw_base + rw.idx * g.raw_slot_bytes;
             if (!is_skip) {
-              mbar_expect_tx(RAW_FULL(rw.idx), g.mt * nk * g.main_boxes * box_bytes);
-              for (int j = 0; j < g.mt; ++j) {
+              mbar_expect_tx(RAW_FULL(rw.idx), MT * nk * g.main_boxes * box_bytes);
+              for (int j = 0; j < MT; ++j) {
                 const int xj = x0m + (j * TILE_M * g.main_origin_mul) / 2;
                 for (int k = 0; k < nk; ++k) {
                   const int c16 = (kb0 + k) * KBLK;
@@ -750,8 +751,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 }
               }
             } else {
-              mbar_expect_tx(RAW_FULL(rw.idx), g.mt * nk * KBLK * g.skip_box_w * 4);
-              for (int j = 0; j < g.mt; ++j) {
+              mbar_expect_tx(RAW_FULL(rw.idx), MT * nk * KBLK * g.skip_box_w * 4);
+              for (int j = 0; j < MT; ++j) {
                 const int xj = x0s + (j * TILE_M * g.skip_origin_mul) / 2;
                 for (int k = 0; k < nk; ++k) {
                   const int c16 = (kb0 + k) * KBLK;
@@ -782,7 +783,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     } else {
       Ring ab(g.ab_slots);
-      const uint32_t b_base = smem_u32(smem + g.off_ab + g.mt * g.kbs * g.a_kb_bytes);
+      const uint32_t b_base = smem_u32(smem + g.off_ab + MT * g.kbs * g.a_kb_bytes);
       for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
         const int tile = tile_first + k_local * tile_stride;
         const int nt = (tile / g.tiles_t) % g.n_tiles;
@@ -822,7 +823,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       mbar_wait(ACC_EMPTY(buf), ((k_local / g.nbuf) & 1) ^ 1);  // epilogue drained this accumulator set
       tc_fence_after();
       PROF_ADD(2, tprev);
-      const uint32_t d_tmem0 = tmem_base + buf * g.mt * g.acc_cols;
+      const uint32_t d_tmem0 = tmem_base + buf * MT * g.acc_cols;
       uint32_t acc = 0;
       uint32_t w16 = w_base16;
       for (int st = 0; st < total_stages; ++st) {
@@ -836,13 +837,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
         const uint32_t unit16 = is_skip ? unit_skip16 : unit_main16;
-        const uint32_t b16 = g.w_resident ? w16 : a16 + g.mt * g.kbs * a_kb16;
+        const uint32_t b16 = g.w_resident ? w16 : a16 + MT * g.kbs * a_kb16;
         w16 += nk * unit16;
         const int taps = is_skip ? 1 : d.ksize;
         const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
         if (elect_one()) {
           if (!(d.reserved_ & 4)) {
-            for (int j = 0; j < g.mt; ++j) {
+            for (int j = 0; j < MT; ++j) {
               const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
               uint32_t accj = acc;  // 0 only for the first MMA of each accumulator of the item
               for (int k = 0; k < nk; ++k) {
@@ -922,8 +923,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       int t = 0;
       bool t_ok = false;
 #pragma unroll 1
-     for (int j = 0; j < g.mt; ++j) {  // the time tiles of this item
-      acc_addr = tmem_base + (buf * g.mt + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
+     for (int j = 0; j < MT; ++j) {  // the time tiles of this item
+      acc_addr = tmem_base + (buf * MT + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
       t = t0 + j * TILE_M + row;
       t_ok = t < d.t_out;
 #pragma unroll 1
@@ -960,7 +961,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         float v[32];
         tmem_ld32(acc_addr + ch * 32, v);
         PROF_ADD(2, tprev);
-        if (j == g.mt - 1 && ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulators back
+        if (j == MT - 1 && ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulators back
           tc_fence_before();
           mbar_arrive(ACC_EMPTY(buf));
           released = true;
@@ -1299,7 +1300,8 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1326,7 +1328,10 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
-  umma::conv_umma_kernel<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
+  if (g.mt == 2)
+    umma::conv_umma_kernel<2><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
+  else
+    umma::conv_umma_kernel<1><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }
