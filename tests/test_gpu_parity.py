@@ -254,3 +254,42 @@ def test_cpu_tensors_fail_loudly():
     m = _diffusion_model("diffusion_unet16", "unet16")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.predictor(torch.zeros(1, 1, 512), torch.zeros(1))
+
+
+# ---------------------------------------------------------------------------
+# BASELINE sizes: unet64, 64000-sample waveforms
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def unet64():
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    m = DiffusionModel("unet", 64)
+    sd = synth.synth_state_dict(synth.shapes_of(m), tag="full64")
+    m.load_state_dict(sd)
+    return m.to(DEV).eval(), sd
+
+
+def test_full_size_forward_vs_oracle(unet64, monkeypatch):
+    """One unet64 forward at T = 64000 (BASELINE configs[1] shape, batch 1) against the CPU oracle."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    m, sd = unet64
+    x = synth.normal("full64/x", (1, 1, 64000))
+    ts = torch.tensor([0.62])
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.unet_predictor(sd, x, ts)
+    got = m.predictor(x.to(DEV), ts.to(DEV)).cpu()
+    assert rel_l2(got, ref) <= 1e-3  # north_star tolerance; measured ~2e-5
+
+
+def test_batch_64_samples_are_independent(unet64, monkeypatch):
+    """Size-independent property at the benchmark batch: sample i of a batch-64 forward equals the same
+    sample run alone (every op on the path is per-sample; only atomic summation order may differ)."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    m, _ = unet64
+    x = synth.normal("full64/xb", (64, 1, 64000)).to(DEV)
+    ts = torch.linspace(0.05, 1.0, 64, device=DEV)
+    full = m.predictor(x, ts)
+    for i in (0, 37, 63):
+        alone = m.predictor(x[i:i + 1].contiguous(), ts[i:i + 1].contiguous())
+        assert rel_l2(alone.cpu(), full[i:i + 1].cpu()) <= 1e-5
+    assert torch.isfinite(full).all()
