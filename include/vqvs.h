@@ -64,6 +64,11 @@ int vqvs_device_info(int* cc, int* sm_count);
  * folded per (sample, channel) by vqvs_gn_finalize.  GELU is the exact erf
  * form (unet.py:341-342).
  */
+/* VqvsConv.reserved_ flag: the producer may accumulate statistics per channel PAIR (both channels' sums go to
+ * the even channel's slot, the odd slot stays as the caller zeroed it).  Valid when every GroupNorm that
+ * consumes them has an even number of channels per group (vqvs_gn_finalize sums over the group anyway). */
+#define VQVS_CONV_PAIR_STATS 1024
+
 typedef struct VqvsConv {
   int32_t batch;
   int32_t c_a, c_b;        /* channels of xa and xb (c_b = 0: no concat) */
@@ -77,7 +82,7 @@ typedef struct VqvsConv {
   int32_t s_a, s_b;        /* channels of the skip sources sa, sb */
   int32_t t_skip;          /* length of sa/sb (the block input; differs from t_in in resize blocks) */
   int32_t skip_resize;     /* VQVS_RESIZE_* applied to the raw skip input: t_out = resize(t_skip) */
-  int32_t reserved_;       /* keeps the pointer block 8-byte aligned */
+  int32_t reserved_;       /* flags: VQVS_CONV_PAIR_STATS; low bits are profiling switches (0 in production) */
   const float* xa;
   const float* xb;
   const float* scale;      /* [batch, c_a+c_b] */

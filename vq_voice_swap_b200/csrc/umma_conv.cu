@@ -23,6 +23,8 @@
 #include <cuda_bf16.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vqvs {
@@ -36,8 +38,9 @@ constexpr int EPI_WARP0 = 0;      // warps 0..7 <-> TMEM lane quarters (warp & 3
 constexpr int MMA_WARP = 8;       // single-thread tcgen05.mma issue
 constexpr int TMA_W_WARP = 9;     // weight image (resident or streamed per K block)
 constexpr int TMA_RAW_WARP = 10;  // raw fp32 activation boxes -> staging ring
-constexpr int XFORM_WARP0 = 11;   // warps 11..19 transform
-constexpr int XFORM_WARPS = 9;    // 8 warps transform the 128 main rows x 2 chunks, the 9th the halo rows
+constexpr int XFORM_WARP0 = 11;   // warps 11..19 transform: warp 11 the halo rows, warps 12..19 the 128 main rows
+constexpr int XFORM_WARPS = 9;
+constexpr int HALO_WARP = XFORM_WARP0;  // shares warpgroup 2 (small register budget) with the MMA / TMA warps
 constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
 constexpr int THREADS = (XFORM_WARP0 + XFORM_WARPS) * 32;
@@ -51,6 +54,8 @@ struct Geo {
   int nkb_main, nkb_skip;   // K blocks (16 channels) of the main taps / of the 1x1 skip
   int pad, rows;            // halo and operand rows (= 128 + 2*pad)
   int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
+  int stack;                // 1: weight rows are [W_hi ; W_lo] (N = 2*n_tile): two MMAs per tap give all four
+                            //    hi/lo products, the epilogue adds the two column halves
   int a_kb_bytes;           // operand bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
   int b_unit_main;          // weight bytes per main K block: ksize taps x hi/lo x 2 chunks x n_tile rows x 16 B
   int b_unit_skip;          // weight bytes per skip K block
@@ -91,8 +96,12 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->b_unit_main = ksize * g->n_tile * 64;
   g->b_unit_skip = g->n_tile * 64;
   g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
+  // Narrow layers: an MMA costs the same ~77 cycles for N = 64 and N = 128 (tools/mma_bench.cu), so stacking
+  // W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs,
+  // which also adds the lo*lo term).
+  g->stack = (g->n_tile == 32 || g->n_tile == 64) ? 1 : 0;
   int cols = 32;
-  while (cols < g->n_tile) cols *= 2;
+  while (cols < (g->stack ? 2 : 1) * g->n_tile) cols *= 2;
   g->acc_cols = cols;
   g->tmem_cols = 2 * cols;
   g->tma = tma ? 1 : 0;
@@ -133,19 +142,22 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->off_raw = off;
   const int left0 = budget - off;
   bool ok = false;
-  for (int cand = 0; cand < 4 && !ok; ++cand) {
+  // stage sizes must be 1, 2 or 4 K blocks (the transform warps split a stage by powers of two)
+  auto sizes_ok = [](int nkb, int kbs) { return nkb == 0 || kbs < 4 || (nkb % 4) != 3; };
+  for (int cand = 0; cand < 6 && !ok; ++cand) {
     // streamed weights: prefer two time tiles per item (mt = 2); resident weights gain nothing from it
-    const int mt = (!g->w_resident && cand < 2) ? 2 : 1;
-    const int kbs = (cand & 1) ? 1 : 2;
-    if (g->w_resident && cand < 2) continue;
+    const int mt = (!g->w_resident && cand < 3) ? 2 : 1;
+    const int kbs = 4 >> (cand % 3);
+    if (g->w_resident && cand < 3) continue;
+    if (!sizes_ok(g->nkb_main, kbs) || !sizes_ok(g->nkb_skip, kbs)) continue;
     if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;
     const int ab_slot = kbs * (mt * g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
     const int raw_slot = mt * kbs * g->raw_kb_bytes;
-    const int min_ab = 2, min_raw = tma ? 3 : 0;
+    const int min_ab = 2, min_raw = tma ? (kbs == 4 ? 2 : 3) : 0;
     if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
-    if (kbs == 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
+    if (kbs >= 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
     int ab = MAX_AB_SLOTS;
-    while (ab > min_ab && left0 - ab * ab_slot < (tma ? 4 * raw_slot : 0)) --ab;
+    while (ab > min_ab && left0 - ab * ab_slot < (tma ? (kbs == 4 ? 3 : 4) * raw_slot : 0)) --ab;
     if (left0 - ab * ab_slot < min_raw * raw_slot) continue;
     if (ab > 4) ab = 4;
     int raw = tma ? (left0 - ab * ab_slot) / raw_slot : 0;
@@ -271,33 +283,65 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 8-column TMEM load WITHOUT the wait (pair with tmem_ld_wait): lets global loads be issued under its latency
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two 16-column loads (e.g. the hi and lo halves of a stacked accumulator) behind one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v, float* w) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr1));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(r[i]);
+    w[i] = __uint_as_float(q[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // prologue math
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 // GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
 // max |error| 4.2e-7 over [-12, 12] in fp32, tighter than ATen's own fp32 GELU (1.2e-6).
-// Two MUFU ops (rcp, ex2) + 11 FP32 ops per element.
+// Two MUFU ops (rcp, ex2) + 12 FP32 ops per element.
 __device__ __forceinline__ float gelu_as(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = ex2_approx(z * z * -1.4426950408889634f);
-  const float half_erfc = (0.5f * t) * (p * e);  // 0.5*erfc(|x|/sqrt2)
-  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return x * phi;
+  // GELU(x) = max(x, 0) - |x| * h(|x|),  h = 0.5*erfc(|x|/sqrt2) = (0.5*poly(t)) * t * exp(-x^2/2),
+  // t = 1 / (1 + (0.3275911/sqrt2) |x|); the 0.5 and the 1/sqrt2 are folded into the constants.
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.2316418882f, ax, 1.0f));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float e = ex2_approx((x * x) * -0.72134752044f);
+  const float h = (t * p) * e;
+  return fmaf(-ax, h, fmaxf(x, 0.f));
 }
 
 // split 8 floats into bf16 hi / lo vectors (16 B each)
@@ -323,14 +367,103 @@ __device__ __forceinline__ void store_rows(const float* v, uint8_t* a_hi, uint8_
   *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
 }
 
-// (scale, shift) for 8 consecutive channels: four float4 = {sc0, sh0, sc1, sh1} ...
+// (scale, shift) for 8 consecutive channels: four float4, one per channel PAIR = {sc0, sc1, sh0, sh1}
+// (pair-major so that the packed fp32x2 path reads {sc0, sc1} and {sh0, sh1} as 64-bit operands)
 __device__ __forceinline__ void affine_gelu8(float* v, const float4* ss) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 p = ss[i];
-    v[2 * i] = gelu_as(fmaf(v[2 * i], p.x, p.y));
-    v[2 * i + 1] = gelu_as(fmaf(v[2 * i + 1], p.z, p.w));
+    v[2 * i] = gelu_as(fmaf(v[2 * i], p.x, p.z));
+    v[2 * i + 1] = gelu_as(fmaf(v[2 * i + 1], p.y, p.w));
   }
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2, two fp32 lanes per instruction) -------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
+
+// Exact-erf GELU (same formula and constants as gelu_as) of 4 packed channel pairs, written stage by stage across
+// the 4 pairs so that the 8 dependency chains interleave: 15 packed/scalar FP instructions + 4 MUFU per PAIR.
+__device__ __forceinline__ void gelu4p(uint64_t* y) {
+  uint64_t nay[4], t[4], q[4], e[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nay[i] = y[i] | 0x8000000080000000ull;  // -|y|
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(nay[i], bcast2(-0.2316418882f), bcast2(1.0f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2(t[i], a, b);
+    t[i] = pack2(rcp_approx(a), rcp_approx(b));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(y[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(e[i], bcast2(-0.72134752044f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2(e[i], a, b);
+    e[i] = pack2(ex2_approx(a), ex2_approx(b));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = fma2(t[i], bcast2(0.5307027145f), bcast2(-0.7265760135f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = fma2(q[i], t[i], bcast2(0.7107068705f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = fma2(q[i], t[i], bcast2(-0.142248368f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = fma2(q[i], t[i], bcast2(0.127414796f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = mul2(q[i], t[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = mul2(q[i], e[i]);  // 0.5*erfc(|y|/sqrt2)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2(y[i], a, b);
+    y[i] = fma2(nay[i], q[i], pack2(fmaxf(a, 0.f), fmaxf(b, 0.f)));
+  }
+}
+
+// 4 packed pairs (8 consecutive channels of one position) -> bf16 hi / lo operand rows (16 B each)
+__device__ __forceinline__ void split4p(const uint64_t* y, uint4* hi, uint4* lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2(y[i], a, b);
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t hf = pack2(__uint_as_float(h[i] << 16), __uint_as_float(h[i] & 0xffff0000u));
+    const uint64_t r = fma2(hf, bcast2(-1.0f), y[i]);  // exact residual
+    float a, b;
+    unpack2(r, a, b);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(a, b);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+  *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct Src {
@@ -410,63 +543,97 @@ struct StageView {
   bool act;
 };
 
-// Row-wise item: the same (8-channel chunk, row) of NK consecutive K blocks -> bf16 hi/lo operand rows.
-// raw / a / ss point at the first K block; the others follow at raw_kb / a_kb bytes and 16 channels.
-template <int NK, bool DOWN>
-__device__ __forceinline__ void transform_rowwise(const StageView& v, const uint8_t* raw0, int raw_kb, uint8_t* a0, int a_kb,
-                                                  const float2* ss0, int chunk, int row) {
-  const int tc = v.tcs + row;
-  float x[NK][8];
-  if (tc >= 0 && tc < v.t_conv) {
-    if (!DOWN) {
-      const int o = (chunk * 8) * v.box_w + (tc - v.x0);
+// Row-wise work of one thread in one stage: rows row_first, row_first + 32, ... (NIT of them) of ONE 8-channel
+// chunk of ONE K block -> bf16 hi/lo operand rows.  The chunk's (scale, shift) are read once into registers as
+// packed pairs; the next row's raw values are fetched before the current row is evaluated.
+// raw / a point at the K block; ss at its 16 (scale, shift) pairs.
+template <bool DOWN>
+__device__ __forceinline__ void load_row8(const StageView& v, const float* raw_c, int tc, float* x, float* w) {
+  if (!DOWN) {
+    const float* raw = raw_c + (tc - v.x0);
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const float* raw = reinterpret_cast<const float*>(raw0 + k * raw_kb) + o;
+    for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
+  } else {
+    int col = 2 * tc - v.x0;
+    const float* raw = raw_c;
+    if (v.boxes == 2 && col >= v.box_w) {
+      col -= v.box_w;
+      raw += KBLK * v.box_w;
+    }
+    raw += col;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[k][e] = raw[e * v.box_w];
-      }
+    for (int e = 0; e < 8; ++e) {
+      const float2 pr = *reinterpret_cast<const float2*>(raw + e * v.box_w);
+      x[e] = pr.x;
+      w[e] = pr.y;
+    }
+  }
+}
+
+template <bool DOWN, int NIT>
+__device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
+                                               int chunk, int row_first) {
+  uint64_t sc[4], sh[4];
+  if (v.act) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 p = reinterpret_cast<const float4*>(ss_kb + chunk * 8)[i];
+      sc[i] = pack2(p.x, p.y);
+      sh[i] = pack2(p.z, p.w);
+    }
+  }
+  const float* raw_c = reinterpret_cast<const float*>(raw_kb) + (chunk * 8) * v.box_w;
+  uint8_t* a_hi = a_kb + chunk * (v.rows * 16);
+  uint8_t* a_lo = a_hi + v.rows * 32;
+  float x[8], w[8], xn[8], wn[8];
+  // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
+  load_row8<DOWN>(v, raw_c, v.tcs + row_first, x, w);
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int row = row_first + 32 * it;
+    const int tc = v.tcs + row;
+    if (it + 1 < NIT) load_row8<DOWN>(v, raw_c, tc + 32, xn, wn);
+    uint64_t y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = pack2(x[2 * i], x[2 * i + 1]);
+    if (v.act) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = fma2(y[i], sc[i], sh[i]);
+      gelu4p(y);
+    }
+    if (DOWN) {
+      uint64_t z[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = pack2(w[2 * i], w[2 * i + 1]);
       if (v.act) {
 #pragma unroll
-        for (int k = 0; k < NK; ++k) affine_gelu8(x[k], reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
+        for (int i = 0; i < 4; ++i) z[i] = fma2(z[i], sc[i], sh[i]);
+        gelu4p(z);
       }
-    } else {
-      int col = 2 * tc - v.x0;
-      int o = (chunk * 8) * v.box_w;
-      if (v.boxes == 2 && col >= v.box_w) {
-        col -= v.box_w;
-        o += KBLK * v.box_w;
-      }
-      o += col;
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const float* raw = reinterpret_cast<const float*>(raw0 + k * raw_kb) + o;
-        float w[8];
+      for (int i = 0; i < 4; ++i) y[i] = fma2(y[i], bcast2(0.5f), mul2(z[i], bcast2(0.5f)));
+    }
+    uint4 hi, lo;
+    split4p(y, &hi, &lo);
+    if (tc < 0 || tc >= v.t_conv) hi = lo = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
+    *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+    if (it + 1 < NIT) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float2 p = *reinterpret_cast<const float2*>(raw + e * v.box_w);
-          x[k][e] = p.x;
-          w[e] = p.y;
-        }
-        if (v.act) {
-          affine_gelu8(x[k], reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
-          affine_gelu8(w, reinterpret_cast<const float4*>(ss0 + k * KBLK + chunk * 8));
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[k][e] = 0.5f * (x[k][e] + w[e]);
+      for (int e = 0; e < 8; ++e) {
+        x[e] = xn[e];
+        if (DOWN) w[e] = wn[e];
       }
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[k][e] = 0.f;
   }
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    uint8_t* a_hi = a0 + k * a_kb + chunk * (v.rows * 16);
-    store_rows(x[k], a_hi, a_hi + v.rows * 32, row);
-  }
+}
+
+template <bool DOWN>
+__device__ __forceinline__ void transform_rows_n(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
+                                                 int chunk, int row_first, int nit) {
+  if (nit == 4) transform_rows<DOWN, 4>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
+  else if (nit == 2) transform_rows<DOWN, 2>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
+  else transform_rows<DOWN, 1>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
 }
 
 // nearest x2: one item = one SOURCE position of one K block -> two operand rows (GELU evaluated once)
@@ -555,14 +722,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const int c_in = d.c_a + d.c_b;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile schedule: round-robin, so that concurrently running CTAs touch neighbouring time tiles
-  const int tile_first = (int)blockIdx.x, tile_stride = (int)gridDim.x;
-  const int n_my_tiles = (g.tiles_total - tile_first + tile_stride - 1) / tile_stride;
-#define TILE_COORDS(tile)                          \
-  const int tx_ = (tile) % g.tiles_t;              \
-  const int nt = ((tile) / g.tiles_t) % g.n_tiles; \
-  const int n = (tile) / (g.tiles_t * g.n_tiles);  \
-  const int t0 = tx_ * (TILE_M * MT);
+  // tile schedule: every CTA owns a contiguous range of work items (sample-major, then N tile, then time), so
+  // the epilogue can keep GroupNorm partial sums in registers across the tiles of a sample
+  const int tiles_lo = g.tiles_total / (int)gridDim.x, tiles_rem = g.tiles_total % (int)gridDim.x;
+  const int tile_first = (int)blockIdx.x * tiles_lo + min((int)blockIdx.x, tiles_rem);
+  const int n_my_tiles = tiles_lo + ((int)blockIdx.x < tiles_rem ? 1 : 0);
+  // (time tile, N tile, sample) of the CTA's first item, advanced incrementally: no division per tile
+  const int tile0_tx = tile_first % g.tiles_t, tile0_nt = (tile_first / g.tiles_t) % g.n_tiles;
+  const int tile0_n = tile_first / (g.tiles_t * g.n_tiles);
+#define TILE_ITER_INIT() int it_tx = tile0_tx, it_nt = tile0_nt, it_n = tile0_n
+#define TILE_COORDS(tile)     \
+  const int nt = it_nt;       \
+  const int n = it_n;         \
+  const int t0 = it_tx * (TILE_M * MT);
+#define TILE_ITER_NEXT() (++it_tx == g.tiles_t ? (it_tx = 0, (++it_nt == g.n_tiles ? (it_nt = 0, ++it_n) : 0)) : 0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RAW_SLOTS; ++i) {
@@ -596,47 +769,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   const uint32_t tmem_base = *tmem_holder;
   const int total_stages = g.main_stages + g.skip_stages;
 
-// Per-role register budgets.  setmaxnreg moves registers inside the CTA's OWN pool (threads x launch
-// registers = 640 x 96 = 61440), so 12 warps x 72 + 8 warps x 128 = 1888 <= 20 x 96 = 1920 per lane must hold
-// (72 / 136 overdraws the pool and the last epilogue warpgroup spins in USETMAXREG.TRY_ALLOC forever).
-#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
-#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 128;")
-  if (warp >= EPI_WARP0 + EPI_WARPS) {
-  REG_DEC();  // one instruction for all three non-epilogue warpgroups (setmaxnreg is warpgroup-collective)
-  if (warp >= XFORM_WARP0) {
+// Register budget: 640 threads x 96 registers (the launch bound) for every role.  Per-role budgets via setmaxnreg
+// were tried (72/128, 56/96/112): the halo transform warp then runs spilling code on the critical path of every
+// stage, and an overdrawn pool deadlocks in USETMAXREG.TRY_ALLOC; a uniform budget is both faster and simpler.
+#define REG_DEC() do { } while (0)  // uniform budget: see above
+#define REG_INC() do { } while (0)
+  auto transform_role = [&](auto halo_c) {
+    constexpr bool HALO = decltype(halo_c)::value;
     const int xtid = threadIdx.x - XFORM_WARP0 * 32, xwarp = warp - XFORM_WARP0;
+    const int mwarp = xwarp - 1;  // 0..7 for the main-row warps
     // =========================== operand producers (transform warps) ===========================
     const Src main_src{d.xa, d.xb, d.c_a, d.c_b, d.t_in, d.t_out, d.resize};
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
-    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && xtid == 0);
-    // this thread's fixed item of a row-wise stage
-    const int my_chunk = xtid >> 7, my_row = xtid & (TILE_M - 1);
-    for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-      const int tile = tile_first + k_local * tile_stride;
+    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && xtid == 32);
+    // per-CTA constants of the two operand sources (main taps / 1x1 skip)
+    StageView vm, vs;
+    vm.rows = vs.rows = g.rows;
+    vm.box_w = g.main_box_w;  vs.box_w = g.skip_box_w;
+    vm.boxes = g.main_boxes;  vs.boxes = 1;
+    vm.n_rows = g.rows;       vs.n_rows = TILE_M;
+    vm.t_src = d.t_in;        vs.t_src = d.t_skip;
+    vm.t_conv = vs.t_conv = d.t_out;
+    vm.resize = d.resize;     vs.resize = d.skip_resize;
+    vm.act = d.act && !(d.reserved_ & 8);
+    vs.act = false;
+    const int main_step = (TILE_M * g.main_origin_mul) / 2, skip_step = (TILE_M * g.skip_origin_mul) / 2;
+    TILE_ITER_INIT();
+    for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
       TILE_COORDS(tile)
       (void)nt;
       if (d.act && n != staged_n) {  // per-sample GroupNorm/FiLM affine
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
-        for (int i = xtid; i < c_in; i += XFORM_WARPS * 32)
-          s_ss[i] = make_float2(d.scale[(size_t)n * c_in + i], d.shift[(size_t)n * c_in + i]);
+        for (int i = xtid; i < c_in / 2; i += XFORM_WARPS * 32) {  // pair-major: {sc0, sc1, sh0, sh1}
+          const float2 sc = *reinterpret_cast<const float2*>(d.scale + (size_t)n * c_in + 2 * i);
+          const float2 sh = *reinterpret_cast<const float2*>(d.shift + (size_t)n * c_in + 2 * i);
+          reinterpret_cast<float4*>(s_ss)[i] = make_float4(sc.x, sc.y, sh.x, sh.y);
+        }
         staged_n = n;
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
       }
-      StageView vm, vs;  // per-tile views of the main taps and of the 1x1 skip (first tile of the item)
-      vm.rows = vs.rows = g.rows;
-      vm.box_w = g.main_box_w;  vs.box_w = g.skip_box_w;
-      vm.boxes = g.main_boxes;  vs.boxes = 1;
-      vm.x0 = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
-      vs.x0 = (t0 * g.skip_origin_mul) / 2;
-      vm.tcs = t0 - g.pad;      vs.tcs = t0;
-      vm.n_rows = g.rows;       vs.n_rows = TILE_M;
-      vm.t_src = d.t_in;        vs.t_src = d.t_skip;
-      vm.t_conv = vs.t_conv = d.t_out;
-      vm.resize = d.resize;     vs.resize = d.skip_resize;
-      vm.act = d.act && !(d.reserved_ & 8);
-      vs.act = false;
+      const int x0m = (t0 / 2) * g.main_origin_mul + g.main_origin_off;  // t0 is a multiple of 128
+      const int x0s = (t0 / 2) * g.skip_origin_mul;
       for (int st = 0; st < total_stages; ++st) {
         PROF_ADD(3, tprev);
         mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
@@ -648,47 +823,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
           PROF_ADD(1, tprev);
-         for (int j = 0; j < MT; ++j) {  // the time tiles of this item share the weights of the stage
-          StageView v = vm;  // by value: keeps the views in registers
-          if (is_skip) v = vs;
-          v.x0 += (j * TILE_M * (is_skip ? g.skip_origin_mul : g.main_origin_mul)) / 2;
-          v.tcs += j * TILE_M;
-          const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes + j * g.kbs * g.raw_kb_bytes;
-          uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
+          StageView v = is_skip ? vs : vm;
+          v.x0 = is_skip ? x0s : x0m;
+          v.tcs = is_skip ? t0 : t0 - g.pad;
+          const int step = is_skip ? skip_step : main_step;
           const float2* ss = s_ss + kb0 * KBLK;
-          if (d.reserved_ & 64) {
-            // ablation: no staging work at all
-          } else if (v.resize == VQVS_RESIZE_UP2) {
-            const int first = v.tcs >> 1;
-            const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
-            for (int i = xtid; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
-              const int q = i / nsrc, j = i - q * nsrc;  // q = (k block, chunk)
-              transform_up2(v, raw + (q >> 1) * g.raw_kb_bytes, a_slot + (q >> 1) * g.a_kb_bytes, ss + (q >> 1) * KBLK, q & 1, first + j);
-            }
-          } else {
-            // warps 0..7: the 128 main rows of both chunks (all K blocks of the stage); last warp: the halo rows
-            const bool down = v.resize == VQVS_RESIZE_DOWN2;
-            if (xwarp < XFORM_WARPS - 1) {
-              if (nk == 2 && !down) {
-                transform_rowwise<2, false>(v, raw, g.raw_kb_bytes, a_slot, g.a_kb_bytes, ss, my_chunk, my_row);
-              } else {
-                for (int k = 0; k < nk; ++k) {
-                  if (down) transform_rowwise<1, true>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
-                  else transform_rowwise<1, false>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, my_chunk, my_row);
-                }
+          // Work split of a row-wise stage: the stage has 2*nk chunks of 8 channels; warps 0..7 each own ONE chunk
+          // (q) and a 128*nk/... slice of the 128 main rows, so the chunk's (scale, shift) live in registers for
+          // the whole stage; the 9th warp transforms the halo rows of every chunk.
+          const int chunks = 2 * nk;                       // 2, 4 or 8 (stage sizes are 1, 2 or 4 K blocks)
+          const int q = mwarp & (chunks - 1);
+          const int row_first = (mwarp / chunks) * (16 * chunks) + lane;  // 8/chunks warps share a chunk
+          for (int j = 0; j < MT; ++j, v.x0 += step, v.tcs += TILE_M) {  // the time tiles of this item share the stage's weights
+            const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes + j * g.kbs * g.raw_kb_bytes;
+            uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
+            if (d.reserved_ & 64) {
+              // ablation: no staging work at all
+            } else if (v.resize == VQVS_RESIZE_UP2) {
+              const int first = v.tcs >> 1;
+              const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
+              for (int i = xtid; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
+                const int qq = i / nsrc, jj = i - qq * nsrc;  // qq = (k block, chunk)
+                transform_up2(v, raw + (qq >> 1) * g.raw_kb_bytes, a_slot + (qq >> 1) * g.a_kb_bytes, ss + (qq >> 1) * KBLK, qq & 1, first + jj);
               }
             } else {
-              const int n_extra = v.n_rows - TILE_M;
-              for (int i = lane; i < nk * 2 * n_extra; i += 32) {
-                const int q = i / n_extra;  // (k block, chunk)
-                const int row = TILE_M + (i - q * n_extra);
-                const int k = q >> 1;
-                if (down) transform_rowwise<1, true>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, q & 1, row);
-                else transform_rowwise<1, false>(v, raw + k * g.raw_kb_bytes, 0, a_slot + k * g.a_kb_bytes, 0, ss + k * KBLK, q & 1, row);
+              const bool down = v.resize == VQVS_RESIZE_DOWN2;
+              if constexpr (!HALO) {
+                const uint8_t* raw_q = raw + (q >> 1) * g.raw_kb_bytes;
+                uint8_t* a_q = a_slot + (q >> 1) * g.a_kb_bytes;
+                const float2* ss_q = ss + (q >> 1) * KBLK;
+                if (down) transform_rows_n<true>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
+                else transform_rows_n<false>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
+              } else {
+                const int n_extra = v.n_rows - TILE_M;
+                for (int i = lane; i < chunks * n_extra; i += 32) {
+                  const int qq = i / n_extra;  // (k block, chunk)
+                  const int row = TILE_M + (i - qq * n_extra);
+                  const int k = qq >> 1;
+                  if (down) transform_rows<true, 1>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row);
+                  else transform_rows<false, 1>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row);
+                }
               }
             }
           }
-         }
         } else {
          for (int j = 0; j < MT; ++j) {
           uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
@@ -717,14 +894,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     }
     PROF_STORE(0);
+  };  // transform_role
+  if (warp > HALO_WARP) {
+    transform_role(std::false_type{});
+  } else if (warp >= EPI_WARP0 + EPI_WARPS) {
+  REG_DEC();  // warpgroup 2 (setmaxnreg is warpgroup-collective)
+  if (warp == HALO_WARP) {
+    transform_role(std::true_type{});
   } else if (warp == TMA_RAW_WARP) {
     // =========================== TMA: raw activation boxes (warp-uniform loop, elected issue) ==========
     if (g.tma) {
       Ring rw(g.raw_slots);
       const uint32_t raw_base = smem_u32(smem + g.off_raw);
       const uint32_t box_bytes = KBLK * g.main_box_w * 4;
-      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-        const int tile = tile_first + k_local * tile_stride;
+      TILE_ITER_INIT();
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         TILE_COORDS(tile)
         (void)nt;
         const int x0m = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
@@ -784,9 +968,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     } else {
       Ring ab(g.ab_slots);
       const uint32_t b_base = smem_u32(smem + g.off_ab + MT * g.kbs * g.a_kb_bytes);
-      for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-        const int tile = tile_first + k_local * tile_stride;
-        const int nt = (tile / g.tiles_t) % g.n_tiles;
+      TILE_ITER_INIT();
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
+        const int nt = it_nt;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
         for (int st = 0; st < total_stages; ++st) {
           const bool is_skip = st >= g.main_stages;
@@ -806,9 +990,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (warp-uniform loop, elected issue) ===========================
-    const uint32_t idesc = make_idesc(g.n_tile);
+    const uint32_t idesc = make_idesc((g.stack ? 2 : 1) * g.n_tile);
     // descriptor = constant fields + (address >> 4); the address field never carries into LBO
-    const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, g.n_tile * 16, 128);
+    const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, (g.stack ? 2 : 1) * g.n_tile * 16, 128);
     const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
     const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
     const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
@@ -854,7 +1038,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   mma_bf16(d_tmem, da_hi, db_hi, idesc, accj);
                   accj = 1;
                   mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
-                  mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+                  if (!g.stack) mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
                 }
               }
             }
@@ -882,6 +1066,135 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const int n_chunks32 = g.n_tile / 32;
     const bool tail16 = (g.n_tile & 31) != 0;
     const bool stats = d.stats_out && !(d.reserved_ & 1);
+    // ---- fast path: N tile of 64 or 128 channels, statistics kept in registers across the CTA's tiles ----
+    // Each thread owns one row (time position) of the tile and NCH x 32 channel columns; it accumulates
+    // (sum, sumsq) per channel PAIR in fp32 registers (2 instructions per element instead of the ~8 of a
+    // per-tile transposing butterfly) and reduces across the warp's 32 rows only when the sample changes or
+    // every STAT_FLUSH_TILES tiles (keeps the fp32 partial sums short), then one fp64 atomic per pair.
+    const bool pair_ok = !stats || (d.reserved_ & VQVS_CONV_PAIR_STATS);
+    const bool fast = pair_ok && !tail16 && (n_chunks32 == EPI_SPLIT || n_chunks32 == 2 * EPI_SPLIT) && !(d.reserved_ & 32);
+    auto run_fast = [&](auto nch_c) {
+      constexpr int NCH = decltype(nch_c)::value;
+      constexpr int STAT_FLUSH_TILES = 32;
+      float s1[NCH][16], s2[NCH][16];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s1[c][i] = s2[c][i] = 0.f;
+      int since_flush = 0;
+      auto flush = [&](int fn, int fnt) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float arr[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            arr[i] = s1[c][i];
+            arr[16 + i] = s2[c][i];
+            s1[c][i] = s2[c][i] = 0.f;
+          }
+          const float r = column_sums32(arr, lane);  // lane l: l < 16 -> sum of pair l, else sumsq of pair l-16
+          const int co = fnt * g.n_tile + (half + EPI_SPLIT * c) * 32 + 2 * (lane & 15);
+          if (!(d.reserved_ & 2)) atomicAdd(d.stats_out + ((size_t)fn * d.c_out + co) * 2 + (lane >> 4), (double)r);
+        }
+        since_flush = 0;
+      };
+      const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
+      const int row = quarter * 32 + lane;
+      TILE_ITER_INIT();
+      for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
+        TILE_COORDS(tile)
+        if (nt != staged_nt) {  // bias slice of this N tile
+          asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
+          for (int i = etid; i < g.n_tile; i += EPI_WARPS * 32) {
+            const int co = nt * g.n_tile + i;
+            float b = d.bias ? d.bias[co] : 0.f;
+            if (d.skip_mode == VQVS_SKIP_CONV1X1 && d.b_skip) b += d.b_skip[co];
+            s_bias[i] = b;
+          }
+          staged_nt = nt;
+          asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
+        }
+        if (stats && (n != stat_n || nt != stat_nt || since_flush >= STAT_FLUSH_TILES)) {
+          if (stat_n >= 0) flush(stat_n, stat_nt);
+          stat_n = n;
+          stat_nt = nt;
+        }
+        ++since_flush;
+        const int buf = k_local % g.nbuf;
+        const uint32_t acc_par = (k_local / g.nbuf) & 1;
+        bool waited = false;
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+          const uint32_t acc_addr = tmem_base + (buf * MT + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
+          const int t = t0 + j * TILE_M + row;
+          const bool t_ok = t < d.t_out;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+              const int c0 = (half + EPI_SPLIT * c) * 32 + sub * 8;  // first column of this 8-wide piece
+              const int co0 = nt * g.n_tile + c0;
+              if (!waited) {
+                mbar_wait(ACC_FULL(buf), acc_par);
+                tc_fence_after();
+                waited = true;
+              }
+              uint32_t vr[8], wr[8];
+              tmem_ld8_nowait(acc_addr + c0, vr);
+              if (g.stack) tmem_ld8_nowait(acc_addr + g.n_tile + c0, wr);
+              float sk[8];
+              if (skip_id && t_ok) {  // issued under the TMEM load latency
+                const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
+                                              : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
+                if (d.skip_resize == VQVS_RESIZE_NONE) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) sk[i] = __ldg(sp + (size_t)i * d.t_skip + t);
+                } else if (d.skip_resize == VQVS_RESIZE_UP2) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) sk[i] = __ldg(sp + (size_t)i * d.t_skip + (t >> 1));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)i * d.t_skip + 2 * t));
+                    sk[i] = 0.5f * (p.x + p.y);
+                  }
+                }
+              }
+              tmem_ld_wait();
+              if (j == MT - 1 && c == NCH - 1 && sub == 3) {  // last TMEM read of the item: hand the accumulators back
+                tc_fence_before();
+                mbar_arrive(ACC_EMPTY(buf));
+              }
+              if (t_ok && !(d.reserved_ & 16)) {
+                const float* bias = s_bias + c0;
+                float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float o = __uint_as_float(vr[i]) + bias[i];
+                  if (g.stack) o += __uint_as_float(wr[i]);
+                  if (skip_id) o += sk[i];
+                  outp[(size_t)i * d.t_out] = o;
+                  v[i] = o;
+                }
+                if (stats && !(d.reserved_ & 128)) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    s1[c][sub * 4 + (i >> 1)] += v[i];
+                    s2[c][sub * 4 + (i >> 1)] = fmaf(v[i], v[i], s2[c][sub * 4 + (i >> 1)]);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if (stats && stat_n >= 0) flush(stat_n, stat_nt);
+    };
+    if (fast) {
+      if (n_chunks32 == EPI_SPLIT) run_fast(std::integral_constant<int, 1>{});
+      else run_fast(std::integral_constant<int, 2>{});
+    } else {
     auto flush_stats = [&](int fn, int fnt) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -894,8 +1207,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
       }
     };
-    for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
-      const int tile = tile_first + k_local * tile_stride;
+    TILE_ITER_INIT();
+    for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
       TILE_COORDS(tile)
       if (nt != staged_nt) {  // bias slice of this N tile
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32));
@@ -933,7 +1246,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (ch >= n_chunks32 || (d.reserved_ & 16)) break;
         const int co0 = nt * g.n_tile + ch * 32;
         // identity-skip operands are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs)
-        float sk[32];
+        float sk[32], sk_lo[32];
         if (skip_id && t_ok) {
           const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
                                         : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
@@ -960,6 +1273,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
         float v[32];
         tmem_ld32(acc_addr + ch * 32, v);
+        if (g.stack) {  // [W_hi ; W_lo] products sit in two column halves
+          tmem_ld32(acc_addr + g.n_tile + ch * 32, sk_lo);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += sk_lo[j];
+        }
         PROF_ADD(2, tprev);
         if (j == MT - 1 && ch + EPI_SPLIT >= n_chunks32 && !(tail16 && half == 0)) {  // last TMEM read of this warp: hand the accumulators back
           tc_fence_before();
@@ -1010,7 +1328,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         float v[16];
         const int cbase = n_chunks32 * 32;
         const bool do_tail = tail16 && half == 0;
-        if (do_tail) tmem_ld16(acc_addr + cbase, v);
+        if (do_tail) tmem_ld16(acc_addr + cbase, v);  // (stacking is never combined with a 16-column tail)
         tc_fence_before();
         mbar_arrive(ACC_EMPTY(buf));
         if (do_tail && !(d.reserved_ & 16)) {
@@ -1043,6 +1361,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       }
     }
     if (stats && stat_n >= 0) flush_stats(stat_n, stat_nt);
+    }  // generic path
     PROF_STORE(12);
     tc_fence_before();
   }
@@ -1052,6 +1371,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     tmem_dealloc(tmem_base, g.tmem_cols);
   }
 #undef TILE_COORDS
+#undef TILE_ITER_INIT
+#undef TILE_ITER_NEXT
 #undef RAW_FULL
 #undef RAW_EMPTY
 #undef B_FULL
@@ -1090,11 +1411,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     long long off = (long long)nt * g.per_tile_bytes;
     if (!skip) off += (long long)kb * g.b_unit_main + (long long)tap * (g.n_tile * 64);
     else off += (long long)g.nkb_main * g.b_unit_main + (long long)kb * g.b_unit_skip;
-    off += (long long)chunk * (g.n_tile * 16) + (long long)row * 16 + e * 2;
+    // un-stacked: [hi: chunk][row][16 B] then [lo: ...]; stacked: [chunk][rows: hi 0..n_tile-1, lo n_tile..][16 B]
+    off += (long long)chunk * ((g.stack ? 2 : 1) * g.n_tile * 16) + (long long)row * 16 + e * 2;
     const __nv_bfloat16 hi = __float2bfloat16_rn(val);
     const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
     *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(img + off + g.n_tile * 32) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(img + off + (g.stack ? g.n_tile * 16 : g.n_tile * 32)) = lo;
   }
 }
 

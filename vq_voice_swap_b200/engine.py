@@ -93,6 +93,14 @@ def _require_cuda(*tensors):
             )
 
 
+def pair_stats_ok(module: torch.nn.Module) -> bool:
+    """True when every GroupNorm of `module` normalises over an even number of channels per group: then the
+    conv epilogues may keep one (sum, sumsq) accumulator per channel PAIR (VQVS_CONV_PAIR_STATS), which halves
+    their register footprint; vqvs_gn_finalize sums over whole groups either way."""
+    norms = [m for m in module.modules() if isinstance(m, torch.nn.GroupNorm)]
+    return bool(norms) and all((m.num_channels // m.num_groups) % 2 == 0 for m in norms)
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -125,6 +133,7 @@ class Plan:
         self.ops = None
         self.n_launch = 0   # kernels launched per run (memsets excluded)
         self.slots = {}     # named structs patched per call
+        self.pair_stats = False  # producers may merge the statistics of channel pairs (see pair_stats_ok)
 
     # -- buffers -------------------------------------------------------------
     def empty(self, *shape, dtype=torch.float32):
@@ -278,6 +287,8 @@ def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, 
             d.w_skip, d.b_skip = L.ptr(skip_proj.weight), L.ptr(skip_proj.bias)
     d.w_packed = L.ptr(packed)
     d.reserved_ = int(os.environ.get("VQVS_DEBUG_FLAGS", "0"))  # kernel ablation switches (profiling only)
+    if plan.pair_stats:
+        d.reserved_ |= L.CONV_PAIR_STATS
     d.out, d.stats_out = out.ptr, out.stats_ptr
     kind = L.OP_CONV_SIMT
     if plan.backend == "umma" and packed is not None and L.load().vqvs_conv1d_umma_supported(C.byref(d)):
@@ -352,6 +363,7 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
     w = weights_for(net, blocks, backend)
     plan = Plan(device, batch, backend)
     plan.weights = w
+    plan.pair_stats = pair_stats_ok(net)
     bc = net.base_channels
     emb_dim = 4 * bc
 
@@ -506,6 +518,7 @@ def build_encoder_plan(net, batch: int, t: int, backend: str) -> Plan:
     w = weights_for(net, blocks, backend)
     plan = Plan(device, batch, backend)
     plan.weights = w
+    plan.pair_stats = pair_stats_ok(net)
     bc = net.base_channels
     alloc = _Alloc(plan, 2 * batch * (bc + 2 * sum(b.out_channels for b in blocks)))
     scratch = _scratch(plan, max(b.channels for b in blocks))
@@ -564,6 +577,7 @@ def run_single_block(blk, x, emb) -> torch.Tensor:
         w = weights_for(blk, [blk], backend)
         plan = Plan(x.device, batch, backend)
         plan.weights = w
+        plan.pair_stats = pair_stats_ok(blk)
         t_out = _resized(t, mode)
         alloc = _Alloc(plan, 2 * batch * (c + 2 * blk.out_channels))
         plan.src = alloc.act(c, t)

@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvqvs.so")
+# VQVS_LIB selects another build of the same sources (profiling variants); there is still no fallback
+LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
 ABI_VERSION = 1
@@ -15,6 +16,7 @@ SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
 OP_CONV_SIMT, OP_CONV_UMMA, OP_GN_FINALIZE, OP_CONV_IN, OP_CONV_OUT = 1, 2, 3, 4, 5
 OP_TIME_EMBED, OP_FILM, OP_MEMSET, OP_DDPM_FINISH = 6, 7, 8, 9
+CONV_PAIR_STATS = 1024  # VqvsConv.reserved_ flag
 
 _i32, _i64, _p = C.c_int32, C.c_int64, C.c_void_p
 
