@@ -68,6 +68,10 @@ int vqvs_device_info(int* cc, int* sm_count);
  * the even channel's slot, the odd slot stays as the caller zeroed it).  Valid when every GroupNorm that
  * consumes them has an even number of channels per group (vqvs_gn_finalize sums over the group anyway). */
 #define VQVS_CONV_PAIR_STATS 1024
+/* bits 12..15 of VqvsConv.reserved_: log2(G), G = 2, 4, 8 or 16 -- the producer may merge the statistics of G
+ * consecutive, G-aligned channels into the first channel's slot (requires VQVS_CONV_PAIR_STATS; 0 means G = 2).
+ * Valid when every consuming GroupNorm group is a union of whole G-granules of this tensor. */
+#define VQVS_CONV_STAT_GRAN_SHIFT 12
 
 typedef struct VqvsConv {
   int32_t batch;

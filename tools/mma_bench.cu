@@ -125,6 +125,69 @@ __global__ void __launch_bounds__(128) bench_kernel(int layout, int n, int shift
   }
 }
 
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t make_idesc_m(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// Clean MMA-rate probe: the whole warp runs the loop with warp-uniform descriptors (no R2UR waterfall), one elected
+// lane issues.  `group` MMAs are issued back to back per commit; ndiff = number of distinct accumulators cycled through.
+__global__ void __launch_bounds__(128) bench2_kernel(int layout, int m, int n, int iters, int group, int ndiff, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t holder;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&holder), 512);
+  for (int i = threadIdx.x; i < 200 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = holder;
+  if (warp == 0) {
+    const int rb = layout == 2 ? 128 : 16;
+    const uint32_t a_base = smem_u32(smem) >> 4, b_base = (smem_u32(smem) + 96 * 1024) >> 4;
+    const uint32_t idesc = make_idesc_m(m, n);
+    const uint64_t a_const = layout ? make_desc(0, 16, 8 * rb, layout, 0) : make_desc(0, (128 + 8) * 16, 128, 0, 0);
+    const uint64_t b_const = layout ? make_desc(0, 16, 8 * rb, layout, 0) : make_desc(0, n * 16, 128, 0, 0);
+    const long long t0 = clock64();
+    uint32_t par = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+        const uint64_t da0 = a_const + a_base, da1 = a_const + (a_base + 544), db0 = b_const + b_base, db1 = b_const + (b_base + 1024);
+        const uint32_t d1 = tmem + (ndiff > 1 ? (uint32_t)n : 0u);
+#pragma unroll 1
+        for (int k = 0; k < group; k += 4) {  // pure back-to-back issue: descriptors are loop-invariant
+          mma_bf16(tmem, da0, db0, idesc, 1);
+          mma_bf16(d1, da1, db0, idesc, 1);
+          mma_bf16(tmem, da0, db1, idesc, 1);
+          mma_bf16(d1, da1, db1, idesc, 1);
+        }
+        mma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), par);
+      par ^= 1;
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // numerics: D[128, n] = A[shift .. shift+128, 0..k) * B[n, k]^T with bf16-exact inputs
 // ---------------------------------------------------------------------------------------------
@@ -211,6 +274,26 @@ int main() {
   CK(cudaMalloc(&d_out, 512 * sizeof(long long)));
   const int layouts[4] = {0, 6, 4, 2};
   const char* names[4] = {"none", "sw32", "sw64", "sw128"};
+  CK(cudaFuncSetAttribute(bench2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  printf("== clean MMA rate (warp-uniform descriptors, elected issue): cycles per MMA incl. one commit+wait per group ==\n");
+  for (int layout : {0, 2})
+    for (int m : {128, 64})
+      for (int n : {64, 128, 256})
+        for (int group : {12, 96})
+          for (int ndiff : {1, 2}) {
+            if (ndiff * n > 512) continue;
+            const int iters = 200;
+            bench2_kernel<<<148, 128, 200 * 1024>>>(layout, m, n, iters, group, ndiff, d_out);
+            CK(cudaDeviceSynchronize());
+            long long h[148];
+            CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+            double avg = 0;
+            for (int i = 0; i < 148; ++i) avg += (double)h[i];
+            avg /= 148;
+            printf("layout=%-5s M=%3d N=%3d group=%2d accumulators=%d : %.1f cycles/MMA\n", layout ? "sw128" : "none", m, n, group, ndiff,
+                   avg / (iters * (double)group));
+          }
+  if (getenv("MMA_BENCH_OLD")) {
   printf("== cycles per MMA (M=128, K=16, bf16), 36 MMAs per group, thread-0 issue -> commit -> wait ==\n");
   for (int grid : {1, 148}) {
     for (int busy : {0, 4000}) {
@@ -232,6 +315,8 @@ int main() {
       }
     }
   }
+  }
+  if (!getenv("MMA_BENCH_OLD")) return 0;
   printf("== numerics: row-shifted start address under swizzle ==\n");
   const int n = 64, k = 64;
   for (int li = 0; li < 4; ++li) {

@@ -570,11 +570,14 @@ __device__ __forceinline__ void load_row8(const StageView& v, const float* raw_c
   }
 }
 
-template <bool DOWN, int NIT>
+// The row loop is deliberately NOT unrolled and every mode is a template parameter: the persistent CTA runs four
+// different role loops at once, and ncu showed instruction-fetch stalls (34 % of all warp samples) as the top stall
+// reason when these loops were unrolled into tens of KB of code.
+template <bool DOWN, bool ACT>
 __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
-                                               int chunk, int row_first) {
+                                               int chunk, int row_first, int nit) {
   uint64_t sc[4], sh[4];
-  if (v.act) {
+  if (ACT) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 p = reinterpret_cast<const float4*>(ss_kb + chunk * 8)[i];
@@ -585,18 +588,17 @@ __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t
   const float* raw_c = reinterpret_cast<const float*>(raw_kb) + (chunk * 8) * v.box_w;
   uint8_t* a_hi = a_kb + chunk * (v.rows * 16);
   uint8_t* a_lo = a_hi + v.rows * 32;
-  float x[8], w[8], xn[8], wn[8];
-  // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
-  load_row8<DOWN>(v, raw_c, v.tcs + row_first, x, w);
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
+#pragma unroll 1
+  for (int it = 0; it < nit; ++it) {
     const int row = row_first + 32 * it;
     const int tc = v.tcs + row;
-    if (it + 1 < NIT) load_row8<DOWN>(v, raw_c, tc + 32, xn, wn);
+    float x[8], w[8];
+    // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
+    load_row8<DOWN>(v, raw_c, tc, x, w);
     uint64_t y[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) y[i] = pack2(x[2 * i], x[2 * i + 1]);
-    if (v.act) {
+    if (ACT) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[i] = fma2(y[i], sc[i], sh[i]);
       gelu4p(y);
@@ -605,7 +607,7 @@ __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t
       uint64_t z[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) z[i] = pack2(w[2 * i], w[2 * i + 1]);
-      if (v.act) {
+      if (ACT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) z[i] = fma2(z[i], sc[i], sh[i]);
         gelu4p(z);
@@ -618,22 +620,14 @@ __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t
     if (tc < 0 || tc >= v.t_conv) hi = lo = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
     *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
-    if (it + 1 < NIT) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        x[e] = xn[e];
-        if (DOWN) w[e] = wn[e];
-      }
-    }
   }
 }
 
 template <bool DOWN>
 __device__ __forceinline__ void transform_rows_n(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
                                                  int chunk, int row_first, int nit) {
-  if (nit == 4) transform_rows<DOWN, 4>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
-  else if (nit == 2) transform_rows<DOWN, 2>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
-  else transform_rows<DOWN, 1>(v, raw_kb, a_kb, ss_kb, chunk, row_first);
+  if (v.act) transform_rows<DOWN, true>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
+  else transform_rows<DOWN, false>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
 }
 
 // nearest x2: one item = one SOURCE position of one K block -> two operand rows (GELU evaluated once)
@@ -860,8 +854,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   const int qq = i / n_extra;  // (k block, chunk)
                   const int row = TILE_M + (i - qq * n_extra);
                   const int k = qq >> 1;
-                  if (down) transform_rows<true, 1>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row);
-                  else transform_rows<false, 1>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row);
+                  if (down) transform_rows_n<true>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
+                  else transform_rows_n<false>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
                 }
               }
             }
@@ -1071,35 +1065,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     // (sum, sumsq) per channel PAIR in fp32 registers (2 instructions per element instead of the ~8 of a
     // per-tile transposing butterfly) and reduces across the warp's 32 rows only when the sample changes or
     // every STAT_FLUSH_TILES tiles (keeps the fp32 partial sums short), then one fp64 atomic per pair.
-    const bool pair_ok = !stats || (d.reserved_ & VQVS_CONV_PAIR_STATS);
-    const bool fast = pair_ok && !tail16 && (n_chunks32 == EPI_SPLIT || n_chunks32 == 2 * EPI_SPLIT) && !(d.reserved_ & 32);
-    auto run_fast = [&](auto nch_c) {
+    // statistics granularity G granted by the caller (1 = per channel): NA = 32 / G accumulators per 32-column chunk
+    const int gran_log2 = !(d.reserved_ & VQVS_CONV_PAIR_STATS) ? 0 : max(1, (d.reserved_ >> VQVS_CONV_STAT_GRAN_SHIFT) & 15);
+    const int nch = n_chunks32 / EPI_SPLIT;  // 32-column chunks per epilogue warp
+    // accumulators per chunk and kind: as few as the granularity allows, at most 32 registers per kind in total
+    const int na = !stats ? 4 : nch == 1 ? 16 : nch == 2 ? (gran_log2 >= 2 ? 8 : 16) : (gran_log2 >= 3 ? 4 : 8);
+    const bool gran_ok = !stats || (gran_log2 >= 1 && (32 >> gran_log2) <= na);
+    const bool fast = gran_ok && !tail16 && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * EPI_SPLIT &&
+                      !(d.reserved_ & 32);
+    auto run_fast = [&](auto nch_c, auto na_c, auto skipk_c) {
       constexpr int NCH = decltype(nch_c)::value;
+      constexpr int NA = decltype(na_c)::value;        // statistics accumulators per 32-column chunk (granularity 32 / NA)
+      constexpr int GSH = NA == 16 ? 1 : NA == 8 ? 2 : 3;  // log2 of the granularity
+      constexpr int SKIPK = decltype(skipk_c)::value;  // 0: no identity skip, 1: identity (none / nearest x2), 2: identity, pooled
       constexpr int STAT_FLUSH_TILES = 32;
-      float s1[NCH][16], s2[NCH][16];
+      float s1[NCH][NA], s2[NCH][NA];
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s1[c][i] = s2[c][i] = 0.f;
+        for (int i = 0; i < NA; ++i) s1[c][i] = s2[c][i] = 0.f;
       int since_flush = 0;
       auto flush = [&](int fn, int fnt) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           float arr[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 32; ++i) arr[i] = 0.f;
+#pragma unroll
+          for (int i = 0; i < NA; ++i) {
             arr[i] = s1[c][i];
-            arr[16 + i] = s2[c][i];
+            arr[NA + i] = s2[c][i];
             s1[c][i] = s2[c][i] = 0.f;
           }
-          const float r = column_sums32(arr, lane);  // lane l: l < 16 -> sum of pair l, else sumsq of pair l-16
-          const int co = fnt * g.n_tile + (half + EPI_SPLIT * c) * 32 + 2 * (lane & 15);
-          if (!(d.reserved_ & 2)) atomicAdd(d.stats_out + ((size_t)fn * d.c_out + co) * 2 + (lane >> 4), (double)r);
+          const float r = column_sums32(arr, lane);  // lane l: l < NA -> sum of granule l, l < 2 NA -> sumsq of granule l - NA
+          const int gi = lane < NA ? lane : lane - NA;
+          const int co = fnt * g.n_tile + (half + EPI_SPLIT * c) * 32 + (gi << GSH);
+          if (lane < 2 * NA && !(d.reserved_ & 2))
+            atomicAdd(d.stats_out + ((size_t)fn * d.c_out + co) * 2 + (lane < NA ? 0 : 1), (double)r);
         }
         since_flush = 0;
       };
-      const bool skip_id = d.skip_mode == VQVS_SKIP_IDENTITY;
       const int row = quarter * 32 + lane;
+      const int skip_shift = d.skip_resize == VQVS_RESIZE_UP2 ? 1 : 0;
+      const bool stack = g.stack != 0;
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         TILE_COORDS(tile)
@@ -1120,6 +1128,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           stat_nt = nt;
         }
         ++since_flush;
+        if (SKIPK != 0) {
+          // L2 prefetch of the NEXT item's identity-skip operands (same sample, next time tiles): lane l covers
+          // channel l of each of this warp's chunks, the 32 (x2 when pooled) positions of the warp's TMEM quarter
+          const int tn = t0 + MT * TILE_M + quarter * 32;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const int co = nt * g.n_tile + (half + EPI_SPLIT * c) * 32 + lane;
+            const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
+                                         : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              const int ts = SKIPK == 2 ? 2 * (tn + j * TILE_M) : (tn + j * TILE_M) >> skip_shift;
+              if (ts < d.t_skip) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + ts));
+                if (SKIPK == 2 && ts + 32 < d.t_skip) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + ts + 32));
+              }
+            }
+          }
+        }
         const int buf = k_local % g.nbuf;
         const uint32_t acc_par = (k_local / g.nbuf) & 1;
         bool waited = false;
@@ -1128,6 +1155,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const uint32_t acc_addr = tmem_base + (buf * MT + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
           const int t = t0 + j * TILE_M + row;
           const bool t_ok = t < d.t_out;
+          // identity-skip operands of one 8-column piece (raw block input, resized on the fly)
+          auto load_skip = [&](int c0_, float* dst) {
+            const int co_ = nt * g.n_tile + c0_;
+            const float* sp = co_ < d.s_a ? d.sa + ((size_t)n * d.s_a + co_) * d.t_skip
+                                          : d.sb + ((size_t)n * d.s_b + (co_ - d.s_a)) * d.t_skip;
+            if (SKIPK == 1) {
+              sp += t >> skip_shift;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = __ldg(sp + (size_t)i * d.t_skip);
+            } else {
+              sp += 2 * t;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)i * d.t_skip));
+                dst[i] = 0.5f * (p.x + p.y);
+              }
+            }
+          };
+          float sk[8], skn[8];
+          // the first piece's operands are requested BEFORE waiting for the accumulator, each later piece's while
+          // the previous piece is being stored (the next item's lines were already prefetched into L2 above)
+          if (SKIPK != 0 && t_ok) load_skip(half * 32, sk);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
 #pragma unroll
@@ -1141,24 +1190,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               }
               uint32_t vr[8], wr[8];
               tmem_ld8_nowait(acc_addr + c0, vr);
-              if (g.stack) tmem_ld8_nowait(acc_addr + g.n_tile + c0, wr);
-              float sk[8];
-              if (skip_id && t_ok) {  // issued under the TMEM load latency
-                const float* sp = co0 < d.s_a ? d.sa + ((size_t)n * d.s_a + co0) * d.t_skip
-                                              : d.sb + ((size_t)n * d.s_b + (co0 - d.s_a)) * d.t_skip;
-                if (d.skip_resize == VQVS_RESIZE_NONE) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) sk[i] = __ldg(sp + (size_t)i * d.t_skip + t);
-                } else if (d.skip_resize == VQVS_RESIZE_UP2) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) sk[i] = __ldg(sp + (size_t)i * d.t_skip + (t >> 1));
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)i * d.t_skip + 2 * t));
-                    sk[i] = 0.5f * (p.x + p.y);
-                  }
-                }
+              if (stack) tmem_ld8_nowait(acc_addr + g.n_tile + c0, wr);
+              constexpr int kLast = 4 * NCH - 1;
+              const bool has_next = c * 4 + sub < kLast;
+              if (SKIPK != 0 && t_ok && has_next) {
+                const int nsub = (sub + 1) & 3, nc = c + (sub == 3 ? 1 : 0);
+                load_skip((half + EPI_SPLIT * nc) * 32 + nsub * 8, skn);
               }
               tmem_ld_wait();
               if (j == MT - 1 && c == NCH - 1 && sub == 3) {  // last TMEM read of the item: hand the accumulators back
@@ -1172,18 +1209,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   float o = __uint_as_float(vr[i]) + bias[i];
-                  if (g.stack) o += __uint_as_float(wr[i]);
-                  if (skip_id) o += sk[i];
+                  if (stack) o += __uint_as_float(wr[i]);
+                  if (SKIPK != 0) o += sk[i];
                   outp[(size_t)i * d.t_out] = o;
                   v[i] = o;
                 }
                 if (stats && !(d.reserved_ & 128)) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    s1[c][sub * 4 + (i >> 1)] += v[i];
-                    s2[c][sub * 4 + (i >> 1)] = fmaf(v[i], v[i], s2[c][sub * 4 + (i >> 1)]);
+                    s1[c][(sub * 8 + i) >> GSH] += v[i];
+                    s2[c][(sub * 8 + i) >> GSH] = fmaf(v[i], v[i], s2[c][(sub * 8 + i) >> GSH]);
                   }
                 }
+              }
+              if (SKIPK != 0 && has_next) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sk[i] = skn[i];
               }
             }
           }
@@ -1192,8 +1233,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       if (stats && stat_n >= 0) flush(stat_n, stat_nt);
     };
     if (fast) {
-      if (n_chunks32 == EPI_SPLIT) run_fast(std::integral_constant<int, 1>{});
-      else run_fast(std::integral_constant<int, 2>{});
+      const int skipk = d.skip_mode != VQVS_SKIP_IDENTITY ? 0 : d.skip_resize == VQVS_RESIZE_DOWN2 ? 2 : 1;
+      auto dispatch_skip = [&](auto nch_c, auto na_c) {
+        if (skipk == 0) run_fast(nch_c, na_c, std::integral_constant<int, 0>{});
+        else if (skipk == 1) run_fast(nch_c, na_c, std::integral_constant<int, 1>{});
+        else run_fast(nch_c, na_c, std::integral_constant<int, 2>{});
+      };
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      using I4 = std::integral_constant<int, 4>;
+      using I8 = std::integral_constant<int, 8>;
+      using I16 = std::integral_constant<int, 16>;
+      if (nch == 1) dispatch_skip(I1{}, I16{});
+      else if (nch == 2 && na == 16) dispatch_skip(I2{}, I16{});
+      else if (nch == 2) dispatch_skip(I2{}, I8{});
+      else if (na == 8) dispatch_skip(I4{}, I8{});
+      else dispatch_skip(I4{}, I4{});
     } else {
     auto flush_stats = [&](int fn, int fnt) {
 #pragma unroll

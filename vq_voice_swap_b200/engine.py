@@ -93,14 +93,6 @@ def _require_cuda(*tensors):
             )
 
 
-def pair_stats_ok(module: torch.nn.Module) -> bool:
-    """True when every GroupNorm of `module` normalises over an even number of channels per group: then the
-    conv epilogues may keep one (sum, sumsq) accumulator per channel PAIR (VQVS_CONV_PAIR_STATS), which halves
-    their register footprint; vqvs_gn_finalize sums over whole groups either way."""
-    norms = [m for m in module.modules() if isinstance(m, torch.nn.GroupNorm)]
-    return bool(norms) and all((m.num_channels // m.num_groups) % 2 == 0 for m in norms)
-
-
 def _f32(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -113,6 +105,8 @@ class Act:
 
     def __init__(self, buf: torch.Tensor, c: int, t: int, stats: Optional[torch.Tensor]):
         self.buf, self.c, self.t, self.stats = buf, c, t, stats
+        self.gran = 0         # gcd of the GroupNorm group sizes (and concat offsets) that consume the statistics
+        self.producer = None  # conv descriptor that writes this tensor
 
     @property
     def ptr(self):
@@ -133,7 +127,7 @@ class Plan:
         self.ops = None
         self.n_launch = 0   # kernels launched per run (memsets excluded)
         self.slots = {}     # named structs patched per call
-        self.pair_stats = False  # producers may merge the statistics of channel pairs (see pair_stats_ok)
+        self.produced = []  # activations written by conv ops (statistics granularity resolved in compile())
 
     # -- buffers -------------------------------------------------------------
     def empty(self, *shape, dtype=torch.float32):
@@ -155,6 +149,11 @@ class Plan:
         return desc
 
     def compile(self):
+        # statistics granularity flags: known only now that every consumer GroupNorm has been emitted
+        for act in self.produced:
+            gran = act.gran & -act.gran if act.gran else 1  # power-of-two part
+            if act.stats is not None and gran >= 2:
+                act.producer.reserved_ |= L.CONV_PAIR_STATS | (min(gran, 16).bit_length() - 1) << L.CONV_STAT_GRAN_SHIFT
         arr = (L.Op * len(self.descs))()
         for i, (kind, desc) in enumerate(self.descs):
             arr[i].kind = kind
@@ -258,6 +257,12 @@ def _emit_gn(plan: Plan, srcs: List[Act], gn: torch.nn.GroupNorm, scale, shift, 
     d.stats_a = srcs[0].stats_ptr
     d.stats_b = srcs[1].stats_ptr if len(srcs) > 1 else 0
     d.gamma, d.beta = L.ptr(gn.weight), L.ptr(gn.bias)
+    # statistics granularity each producer may use: groups of the concatenated tensor must be unions of whole
+    # producer granules, so a source starting at channel offset `off` can merge gcd(group size, off) channels
+    gs, off = (d.c_a + d.c_b) // gn.num_groups, 0
+    for src in srcs:
+        src.gran = math.gcd(src.gran, math.gcd(gs, off))
+        off += src.c
     d.film, d.film_stride = film_ptr, film_stride
     d.scale, d.shift = L.ptr(scale), L.ptr(shift)
     plan.add(L.OP_GN_FINALIZE, d)
@@ -287,9 +292,9 @@ def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, 
             d.w_skip, d.b_skip = L.ptr(skip_proj.weight), L.ptr(skip_proj.bias)
     d.w_packed = L.ptr(packed)
     d.reserved_ = int(os.environ.get("VQVS_DEBUG_FLAGS", "0"))  # kernel ablation switches (profiling only)
-    if plan.pair_stats:
-        d.reserved_ |= L.CONV_PAIR_STATS
     d.out, d.stats_out = out.ptr, out.stats_ptr
+    out.producer = d
+    plan.produced.append(out)
     kind = L.OP_CONV_SIMT
     if plan.backend == "umma" and packed is not None and L.load().vqvs_conv1d_umma_supported(C.byref(d)):
         kind = L.OP_CONV_UMMA
@@ -363,7 +368,6 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
     w = weights_for(net, blocks, backend)
     plan = Plan(device, batch, backend)
     plan.weights = w
-    plan.pair_stats = pair_stats_ok(net)
     bc = net.base_channels
     emb_dim = 4 * bc
 
@@ -518,7 +522,6 @@ def build_encoder_plan(net, batch: int, t: int, backend: str) -> Plan:
     w = weights_for(net, blocks, backend)
     plan = Plan(device, batch, backend)
     plan.weights = w
-    plan.pair_stats = pair_stats_ok(net)
     bc = net.base_channels
     alloc = _Alloc(plan, 2 * batch * (bc + 2 * sum(b.out_channels for b in blocks)))
     scratch = _scratch(plan, max(b.channels for b in blocks))
@@ -577,7 +580,6 @@ def run_single_block(blk, x, emb) -> torch.Tensor:
         w = weights_for(blk, [blk], backend)
         plan = Plan(x.device, batch, backend)
         plan.weights = w
-        plan.pair_stats = pair_stats_ok(blk)
         t_out = _resized(t, mode)
         alloc = _Alloc(plan, 2 * batch * (c + 2 * blk.out_channels))
         plan.src = alloc.act(c, t)

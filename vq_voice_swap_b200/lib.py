@@ -17,6 +17,7 @@ OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
 OP_CONV_SIMT, OP_CONV_UMMA, OP_GN_FINALIZE, OP_CONV_IN, OP_CONV_OUT = 1, 2, 3, 4, 5
 OP_TIME_EMBED, OP_FILM, OP_MEMSET, OP_DDPM_FINISH = 6, 7, 8, 9
 CONV_PAIR_STATS = 1024  # VqvsConv.reserved_ flag
+CONV_STAT_GRAN_SHIFT = 12  # bits 12..15 of VqvsConv.reserved_: log2 of the statistics granularity
 
 _i32, _i64, _p = C.c_int32, C.c_int64, C.c_void_p
 
