@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t make_idesc_m(int m, int n) {
 }
 // Clean MMA-rate probe: the whole warp runs the loop with warp-uniform descriptors (no R2UR waterfall), one elected
 // lane issues.  `group` MMAs are issued back to back per commit; ndiff = number of distinct accumulators cycled through.
-__global__ void __launch_bounds__(128) bench2_kernel(int layout, int m, int n, int iters, int group, int ndiff, long long* out) {
+__global__ void __launch_bounds__(128) bench2_kernel(int layout, int m, int n, int iters, int group, int ndiff, long long* out, int ashift = 0, int bshift = 0, int contend = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t holder;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) bench2_kernel(int layout, int m, int n, i
     uint32_t par = 0;
     for (int it = 0; it < iters; ++it) {
       if (elect_one()) {
-        const uint64_t da0 = a_const + a_base, da1 = a_const + (a_base + 544), db0 = b_const + b_base, db1 = b_const + (b_base + 1024);
+        const uint64_t da0 = a_const + (a_base + ashift), da1 = a_const + (a_base + 544 + 2 * ashift), db0 = b_const + (b_base + bshift), db1 = b_const + (b_base + 1024 + bshift);
         const uint32_t d1 = tmem + (ndiff > 1 ? (uint32_t)n : 0u);
 #pragma unroll 1
         for (int k = 0; k < group; k += 4) {  // pure back-to-back issue: descriptors are loop-invariant
@@ -179,6 +179,31 @@ __global__ void __launch_bounds__(128) bench2_kernel(int layout, int m, int n, i
     }
     const long long t1 = clock64();
     if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    *reinterpret_cast<volatile uint32_t*>(&holder) = 0xffffffffu;  // stop the contending warps
+  } else if (contend == 1) {
+    uint32_t acc = 0;
+    while (*reinterpret_cast<volatile uint32_t*>(&holder) != 0xffffffffu) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(tmem + ((uint32_t)(warp * 32) << 16) + 256 + (acc & 127)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += r[0] + 16;
+    }
+    if (acc == 0x1234567) out[300] = 1;
+  } else if (contend == 2) {
+    const uint32_t p = smem_u32(smem + 160 * 1024);
+    uint32_t x = 0, y = 1, z = 2, w = 3, i = 0;
+    while (*reinterpret_cast<volatile uint32_t*>(&holder) != 0xffffffffu) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(p + (((threadIdx.x + i * 96) & 1023) << 4)));
+      x ^= a0; y ^= a1; z ^= a2; w ^= a3;
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(p + (((threadIdx.x * 7 + i) & 1023) << 4)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+      ++i;
+    }
+    if (x == 0x12345) out[200] = 1;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -293,6 +318,33 @@ int main() {
             printf("layout=%-5s M=%3d N=%3d group=%2d accumulators=%d : %.1f cycles/MMA\n", layout ? "sw128" : "none", m, n, group, ndiff,
                    avg / (iters * (double)group));
           }
+  printf("== effect of 16-byte-granular operand start shifts (conv taps) at the true pipe rate, layout none, M=128 ==\n");
+  for (int n : {64, 128, 256})
+    for (int ashift : {0, 1, 2, 4, 8})
+      for (int bshift : {0, 1}) {
+        const int iters = 200, group = 96;
+        bench2_kernel<<<148, 128, 200 * 1024>>>(0, 128, n, iters, group, 1, d_out, ashift, bshift);
+        CK(cudaDeviceSynchronize());
+        long long h[148];
+        CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < 148; ++i) avg += (double)h[i];
+        avg /= 148;
+        printf("N=%3d A start +%d x16B, B start +%d x16B : %.1f cycles/MMA\n", n, ashift, bshift, avg / (iters * (double)group));
+      }
+  printf("== contention: 3 other warps running tcgen05.ld (1) or LDS/STS.128 (2) while the MMAs run; layout none, M=128 ==\n");
+  for (int n : {64, 128, 256})
+    for (int contend : {0, 1, 2}) {
+      const int iters = 200, group = 96;
+      bench2_kernel<<<148, 128, 200 * 1024>>>(0, 128, n, iters, group, 1, d_out, 0, 0, contend);
+      CK(cudaDeviceSynchronize());
+      long long h[148];
+      CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+      double avg = 0;
+      for (int i = 0; i < 148; ++i) avg += (double)h[i];
+      avg /= 148;
+      printf("N=%3d contend=%d : %.1f cycles/MMA\n", n, contend, avg / (iters * (double)group));
+    }
   if (getenv("MMA_BENCH_OLD")) {
   printf("== cycles per MMA (M=128, K=16, bf16), 36 MMAs per group, thread-0 issue -> commit -> wait ==\n");
   for (int grid : {1, 148}) {

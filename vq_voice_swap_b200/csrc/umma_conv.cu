@@ -715,7 +715,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
   const int c_in = d.c_a + d.c_b;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches are uniform and the
+  // MMA / TMA warps can keep their loop state and descriptors in uniform registers (no R2UR per tcgen05.mma)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // tile schedule: every CTA owns a contiguous range of work items (sample-major, then N tile, then time), so
   // the epilogue can keep GroupNorm partial sums in registers across the tiles of a sample
   const int tiles_lo = g.tiles_total / (int)gridDim.x, tiles_rem = g.tiles_total % (int)gridDim.x;
@@ -1019,24 +1021,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         w16 += nk * unit16;
         const int taps = is_skip ? 1 : d.ksize;
         const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
-        if (elect_one()) {
-          if (!(d.reserved_ & 4)) {
-            for (int j = 0; j < MT; ++j) {
-              const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
-              uint32_t accj = acc;  // 0 only for the first MMA of each accumulator of the item
-              for (int k = 0; k < nk; ++k) {
-#pragma unroll 3
-                for (int tap = 0; tap < taps; ++tap) {
-                  const uint64_t da_hi = a_const + (a16 + (j * g.kbs + k) * a_kb16 + tap * tap_rows);
-                  const uint64_t db_hi = b_const + (b16 + k * unit16 + tap * b_tap_off);
-                  mma_bf16(d_tmem, da_hi, db_hi, idesc, accj);
-                  accj = 1;
-                  mma_bf16(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1);
-                  if (!g.stack) mma_bf16(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1);
+        // Descriptors advance by warp-uniform adds computed by ALL lanes (uniform datapath); only the tcgen05 instructions
+        // themselves sit under the elected-lane predicate.  (With the arithmetic inside the elected branch the compiler
+        // built every descriptor in vector registers and moved it over with R2UR: ~100+ cycles of scalar work per MMA,
+        // twice the 67 cycles the tensor pipe needs -- tools/mma_bench.cu.)
+        const bool issue = elect_one();
+        const bool do_mma = !(d.reserved_ & 4);
+        uint64_t da_j = a_const + a16;
+        const uint64_t db_0 = b_const + b16;
+        const uint32_t a_step_j = g.kbs * a_kb16;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
+          uint32_t accj = acc;  // 0 only for the first MMA of each accumulator of the item
+          uint64_t da_k = da_j, db_k = db_0;
+#pragma unroll 1
+          for (int k = 0; k < nk; ++k) {
+            uint64_t da = da_k, db = db_k;
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+              if (tap < taps) {
+                if (issue && do_mma) {
+                  mma_bf16(d_tmem, da, db, idesc, accj);
+                  mma_bf16(d_tmem, da + a_lo_off, db, idesc, 1);
+                  if (!g.stack) mma_bf16(d_tmem, da, db + b_lo_off, idesc, 1);
                 }
+                accj = 1;
+                da += tap_rows;
+                db += b_tap_off;
               }
             }
+            da_k += a_kb16;
+            db_k += unit16;
           }
+          da_j += a_step_j;
+        }
+        if (issue) {
           mma_commit(AB_EMPTY(ab.idx));
           if (st == total_stages - 1) mma_commit(ACC_FULL(buf));
         }
@@ -1184,9 +1204,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               const int c0 = (half + EPI_SPLIT * c) * 32 + sub * 8;  // first column of this 8-wide piece
               const int co0 = nt * g.n_tile + c0;
               if (!waited) {
+                PROF_ADD(1, tprev);
                 mbar_wait(ACC_FULL(buf), acc_par);
                 tc_fence_after();
                 waited = true;
+                PROF_ADD(0, tprev);
               }
               uint32_t vr[8], wr[8];
               tmem_ld8_nowait(acc_addr + c0, vr);
