@@ -335,3 +335,55 @@ def vqvae_decode(
     cond_seq = vq_embed(sd["vq.dictionary"], codes) if codes.dim() == 2 else codes
     pred = lambda xs, ts: unet_predictor(sd, xs, ts, cond=cond_seq, labels=labels)
     return ddpm_sample(make_alpha_bar(schedule_name), x_T, pred, steps, noises, constrain=constrain)
+
+
+# ---------------------------------------------------------------------------
+# Classifier guidance (config 5) -- models/classifier.py:18-191, sample_diffusion.py:34-42
+# ---------------------------------------------------------------------------
+def attention_pool(x: torch.Tensor, sd: SD, p: str, head_channels: int = 64) -> torch.Tensor:
+    """AttentionPool1d.forward + QKVAttention.forward (models/classifier.py:153-191): zero token first,
+    1x1 qkv conv, per-head softmax(q k^T) v with ch^-1/4 applied to q and k, 1x1 projection, take t = 0."""
+    n, c, _ = x.shape
+    heads = c // min(c, head_channels)
+    ch = c // heads
+    x = torch.cat([torch.zeros_like(x[..., :1]), x], dim=-1)
+    qkv = F.conv1d(x, sd[p + "qkv_proj.weight"], sd[p + "qkv_proj.bias"])
+    q, k, v = qkv.chunk(3, dim=1)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    length = x.shape[-1]
+    w = torch.einsum("bct,bcs->bts", (q * scale).reshape(n * heads, ch, length), (k * scale).reshape(n * heads, ch, length))
+    w = torch.softmax(w, dim=-1)
+    a = torch.einsum("bts,bcs->bct", w, v.reshape(n * heads, ch, length)).reshape(n, -1, length)
+    return F.conv1d(a, sd[p + "c_proj.weight"], sd[p + "c_proj.bias"])[..., 0]
+
+
+def classifier_logits(sd: SD, x: torch.Tensor, ts: torch.Tensor, channel_mult: Sequence[int] = DEFAULT_MULT,
+                      depth_mult: int = 2) -> torch.Tensor:
+    """Classifier.forward (models/classifier.py:31-36) over ClassifierStem.forward (:111-121): every level ends with a
+    downsampling ResBlock (:84-99), then GN -> GELU -> attention pool -> GELU -> Linear."""
+    p = "stem."
+    emb = time_embedding(ts, sd, p)
+    h = conv(x, sd, p + "in_conv")
+    bi = 0
+    for _ in channel_mult:
+        for _ in range(depth_mult):
+            h = resblock(h, emb, sd, f"{p}blocks.{bi}.")
+            bi += 1
+        h = resblock(h, emb, sd, f"{p}blocks.{bi}.", scale_factor=0.5)
+        bi += 1
+    h = gelu(gn(h, sd, p + "out.0.0"))
+    h = attention_pool(h, sd, p + "out.1.")
+    return F.linear(gelu(h), sd["out.1.weight"], sd["out.1.bias"])
+
+
+def classifier_cond_fn(sd: SD, labels: torch.Tensor, scale: float = 1.0, **kw) -> Callable:
+    """cond_fn of sample_diffusion.py:34-42: scale * d/dx sum_n log softmax(logits)[n, label_n]."""
+
+    def cond_fn(x, ts):
+        with torch.enable_grad():
+            xg = x.detach().clone().requires_grad_()
+            logp = F.log_softmax(classifier_logits(sd, xg, ts, **kw), dim=-1)
+            grads = torch.autograd.grad(logp[range(len(xg)), labels].sum(), xg)[0]
+        return grads.detach() * scale
+
+    return cond_fn

@@ -4,7 +4,11 @@ Generate the golden vectors in this directory from the LIVE, UNMODIFIED referenc
 Run in the build container only (the reference is mounted at /root/reference
 there and exists nowhere else):
 
-    PYTHONPATH=/root/reference:/root/repo python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            (everything)
+    python tests/golden/make_golden.py classifier (classifier vectors + key table only)
+
+The script puts /root/reference FIRST on sys.path so that `vq_voice_swap` resolves to the reference and not to
+this repository's drop-in namespace of the same name.
 
 Inputs and weights are pure functions of their names
 (vq_voice_swap_b200.synth), so only the reference's OUTPUTS are stored.  The
@@ -19,7 +23,10 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != os.path.dirname(os.path.dirname(HERE))]
+sys.path.insert(0, HERE)
+sys.path.insert(0, "/root/reference")
+sys.path.append(os.path.dirname(os.path.dirname(HERE)))  # for vq_voice_swap_b200.synth only
 
 import vq_voice_swap  # noqa: E402  (must resolve to the reference)
 
@@ -27,6 +34,7 @@ assert vq_voice_swap.__file__.startswith("/root/reference"), vq_voice_swap.__fil
 
 from vq_voice_swap.diffusion import Diffusion, make_schedule  # noqa: E402
 from vq_voice_swap.diffusion_model import DiffusionModel  # noqa: E402
+from vq_voice_swap.models.classifier import Classifier  # noqa: E402
 from vq_voice_swap.models.unet import ResBlock, UNetEncoder  # noqa: E402
 from vq_voice_swap.vq import VQ  # noqa: E402
 from vq_voice_swap.vq_vae import VQVAE  # noqa: E402
@@ -158,6 +166,33 @@ def vqvae_small():
     save("vqvae_bc16.npz", codes=codes.numpy(), encoder_out=enc_out.numpy(), audio=audio.numpy())
 
 
+def classifier_small():
+    """Classifier logits, the guidance gradient of sample_diffusion.py:34-42, and one guided ddpm_previous."""
+    import torch.nn.functional as F
+
+    torch.set_grad_enabled(True)
+    clf = Classifier(num_labels=7, base_channels=16).eval()
+    synth.load_synth(clf, tag="clf16")
+    x = synth.normal("clf16/x", (2, 1, 1024))
+    ts = torch.tensor([0.8, 0.25])
+    labels = torch.tensor([3, 6])
+    logits = clf(x, ts)
+
+    def cond_fn(xx, tt):
+        with torch.enable_grad():
+            xx = xx.detach().clone().requires_grad_()
+            logp = F.log_softmax(clf(xx, tt), dim=-1)
+            return torch.autograd.grad(logp[range(len(xx)), labels].sum(), xx)[0].detach() * 2.5
+
+    grad = cond_fn(x, ts)
+    diff = Diffusion(make_schedule("exp"))
+    eps = synth.normal("clf16/eps", (2, 1, 1024))
+    noise = synth.normal("clf16/noise", (2, 1, 1024))
+    prev = diff.ddpm_previous(x, ts, 0.02, eps, noise=noise, cond_fn=cond_fn)
+    torch.set_grad_enabled(False)
+    save("classifier_bc16.npz", logits=logits.detach().numpy(), grad=grad.numpy(), prev=prev.numpy())
+
+
 def keys():
     specs = {
         "diffusion_unet32": DiffusionModel("unet", 32),
@@ -166,6 +201,8 @@ def keys():
         "vqvae_unet32": VQVAE(base_channels=32, pred_name="unet", num_labels=8),
         "diffusion_unet16": DiffusionModel("unet", 16),
         "vqvae16": VQVAE(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet"),
+        "classifier16": Classifier(num_labels=7, base_channels=16),
+        "classifier32": Classifier(num_labels=100, base_channels=32),
     }
     table = {
         n: [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()] for n, m in specs.items()
@@ -181,9 +218,14 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["keys"]:
         keys()
         sys.exit(0)
+    if sys.argv[1:] == ["classifier"]:
+        classifier_small()
+        keys()
+        sys.exit(0)
     resblocks()
     unet_small()
     vq_cases()
     ddpm()
     vqvae_small()
+    classifier_small()
     keys()

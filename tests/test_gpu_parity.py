@@ -198,6 +198,75 @@ def test_ddpm_previous_golden(golden, name):
     assert rel_l2(y.cpu(), golden("ddpm.npz")[name]) <= 5e-6
 
 
+def _guidance(labels, scale):
+    """cond_fn exactly as reference sample_diffusion.py:34-42, over this package's Classifier on the GPU."""
+    import torch.nn.functional as F
+
+    from vq_voice_swap_b200.classifier import Classifier
+
+    clf = Classifier(num_labels=7, base_channels=16).eval()
+    clf.load_state_dict(model_sd("classifier16", "clf16"))
+    clf = clf.to(DEV)
+
+    def cond_fn(x, ts):
+        with torch.enable_grad():
+            x = x.detach().clone().requires_grad_()
+            logp = F.log_softmax(clf(x, ts), dim=-1)
+            return torch.autograd.grad(logp[range(len(x)), labels].sum(), x)[0].detach() * scale
+
+    return clf, cond_fn
+
+
+def test_classifier_guided_step_golden(golden):
+    """Config 5's inner step: epsilon -> classifier-gradient shift -> x_{t-1}, against the live reference.
+    The classifier itself runs under ATen autograd on the GPU (TF32 convs disabled for the comparison)."""
+    g = golden("classifier_bc16.npz")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        labels = torch.tensor([3, 6], device=DEV)
+        clf, cond_fn = _guidance(labels, 2.5)
+        x = synth.normal("clf16/x", (2, 1, 1024)).to(DEV)
+        ts = torch.tensor([0.8, 0.25], device=DEV)
+        assert rel_l2(clf(x, ts).detach().cpu(), g["logits"]) <= 1e-4
+        assert rel_l2(cond_fn(x, ts).cpu(), g["grad"]) <= 1e-3
+        eps = synth.normal("clf16/eps", (2, 1, 1024)).to(DEV)
+        noise = synth.normal("clf16/noise", (2, 1, 1024)).to(DEV)
+        prev = _diffusion("exp").ddpm_previous(x, ts, 0.02, eps, noise=noise, cond_fn=cond_fn)
+        assert rel_l2(prev.cpu(), g["prev"]) <= 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("backend", ["umma"])
+def test_classifier_guided_sampling_matches_oracle(monkeypatch, backend):
+    """sample_diffusion.py with --classifier-path (config 5) on a small model: fused UNet steps + guidance shift
+    through ddpm_sample, against the oracle loop with the same injected noise."""
+    monkeypatch.setenv("VQVS_BACKEND", backend)
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        m = DiffusionModel("unet", 16).eval()
+        sd = model_sd("diffusion_unet16", "unet16")
+        m.load_state_dict(sd)
+        m = m.to(DEV)
+        labels = torch.tensor([3, 6])
+        _, cond_fn = _guidance(labels.to(DEV), 1.0)
+        x_T = synth.normal("guided/x_T", (2, 1, 1024))
+        steps = 3
+        noises = [synth.normal(f"guided/noise{i}", x_T.shape) for i in range(steps)]
+        _Noise("guided", monkeypatch)
+        y = m.diffusion.ddpm_sample(x_T.to(DEV), m.predictor, steps, cond_fn=cond_fn)
+        monkeypatch.undo()
+        ref = O.ddpm_sample(O.make_alpha_bar("exp"), x_T, lambda x, t: O.unet_predictor(sd, x, t), steps, noises,
+                            cond_fn=O.classifier_cond_fn(model_sd("classifier16", "clf16"), labels, 1.0))
+        assert rel_l2(y.cpu(), ref) <= 1e-3
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 class _Noise:
     """Same injection as make_golden._Inject, on the device."""
 

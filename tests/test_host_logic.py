@@ -2,6 +2,7 @@
 mirrors match the C structs, and the host modules keep the reference's API surface."""
 
 import ctypes as C
+import json
 import os
 import re
 import subprocess
@@ -80,7 +81,15 @@ STATE_TABLES = {
     "diffusion_unet16_dropout": lambda: _dm("unet", 16, dropout=0.1),
     "vqvae_unet32": lambda: _vqvae(base_channels=32, pred_name="unet", num_labels=8),
     "vqvae16": lambda: _vqvae(base_channels=16, num_labels=3, cond_mult=3, dictionary_size=64, pred_name="unet"),
+    "classifier16": lambda: _classifier(num_labels=7, base_channels=16),
+    "classifier32": lambda: _classifier(num_labels=100, base_channels=32),
 }
+
+
+def _classifier(**k):
+    from vq_voice_swap_b200.classifier import Classifier
+
+    return Classifier(**k)
 
 
 def _dm(*a, **k):
@@ -100,7 +109,7 @@ def test_state_dict_layout_equals_reference(name):
     m = STATE_TABLES[name]()
     mine = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
     assert mine == key_table()[name]
-    assert m.save_kwargs() == key_table()["save_kwargs"][name]
+    assert json.loads(json.dumps(m.save_kwargs())) == key_table()["save_kwargs"][name]  # (JSON turns tuples into lists)
 
 
 def test_checkpoint_roundtrip(tmp_path):
@@ -173,3 +182,37 @@ def test_reference_namespace_shim():
 
     assert vq_voice_swap.__file__.startswith(ROOT)
     assert DiffusionModel is type(_dm("unet", 16)) and VQVAE.__mro__[1] is DiffusionModel
+
+
+def test_classifier_matches_reference_on_cpu(golden):
+    """The guidance classifier is evaluated by ATen under autograd (any device): logits and the guidance
+    gradient of reference sample_diffusion.py:34-42 against the live reference's outputs."""
+    import torch.nn.functional as F
+
+    from helpers import model_sd, rel_l2
+    from vq_voice_swap_b200 import synth
+
+    g = golden("classifier_bc16.npz")
+    clf = _classifier(num_labels=7, base_channels=16).eval()
+    clf.load_state_dict(model_sd("classifier16", "clf16"))
+    x = synth.normal("clf16/x", (2, 1, 1024))
+    ts = torch.tensor([0.8, 0.25])
+    labels = torch.tensor([3, 6])
+    assert rel_l2(clf(x, ts).detach(), g["logits"]) <= 1e-5
+    assert rel_l2(clf(x, ts, use_checkpoint=True).detach(), g["logits"]) <= 1e-5
+    xg = x.clone().requires_grad_()
+    logp = F.log_softmax(clf(xg, ts), dim=-1)
+    grad = torch.autograd.grad(logp[range(2), labels].sum(), xg)[0] * 2.5
+    assert rel_l2(grad, g["grad"]) <= 1e-4
+
+
+def test_classifier_zero_head_and_checkpoint_roundtrip(tmp_path):
+    torch.manual_seed(0)
+    clf = _classifier(num_labels=5, base_channels=16)
+    assert float(clf.out[1].weight.abs().max()) == 0.0  # reference models/classifier.py:27-29
+    path = str(tmp_path / "clf.pt")
+    clf.save(path)
+    again = type(clf).load(path)
+    assert again.save_kwargs() == clf.save_kwargs() and again.num_labels == 5
+    pred = _dm("unet", 16).predictor
+    assert clf.stem.load_from_predictor(pred) > 0  # reference models/classifier.py:123-130

@@ -99,3 +99,19 @@ def test_vqvae_roundtrip(golden):
     noises = [synth.normal(f"vqvae16/decode/noise{i}", (2, 1, 512)) for i in range(2)]
     audio = O.vqvae_decode(sd, "exp", codes, torch.tensor([2, 0]), 3, x_T, noises, constrain=True)
     assert rel_l2(audio, g["audio"]) <= 1e-5
+
+
+def test_classifier_logits_gradient_and_guided_step(golden):
+    """Classifier guidance (config 5): logits, d log p / d x and one guided ddpm_previous vs the live reference."""
+    g = golden("classifier_bc16.npz")
+    sd = model_sd("classifier16", "clf16")
+    x = synth.normal("clf16/x", (2, 1, 1024))
+    ts = torch.tensor([0.8, 0.25])
+    labels = torch.tensor([3, 6])
+    assert rel_l2(O.classifier_logits(sd, x, ts).detach(), g["logits"]) <= TOL
+    cond_fn = O.classifier_cond_fn(sd, labels, scale=2.5)
+    assert rel_l2(cond_fn(x, ts), g["grad"]) <= 1e-5
+    eps = synth.normal("clf16/eps", (2, 1, 1024))
+    noise = synth.normal("clf16/noise", (2, 1, 1024))
+    prev = O.ddpm_previous(O.make_alpha_bar("exp"), x, ts, 0.02, eps, noise, cond_fn=cond_fn)
+    assert rel_l2(prev, g["prev"]) <= 1e-5

@@ -12,6 +12,6 @@ timeout -s KILL 600 python bench.py --impl reference --steps 2 --warmup 1 > $out
 timeout -s KILL 300 python tools/op_profile.py > $out/op_profile.txt 2>&1
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file $out/launches.csv \
     python bench.py --steps 1 --warmup 1 --batch 64 --diffusion-steps 3 --no-cpu-baseline > $out/ncu_launches.log 2>&1
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 10 -c 6 -o $out/conv_umma \
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 10 -c 3 -o $out/conv_umma \
     python bench.py --steps 1 --warmup 1 --batch 64 --diffusion-steps 1 --no-cpu-baseline > $out/ncu_full.log 2>&1
 ls -la $out
