@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 1
+#define VQVS_ABI_VERSION 2
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -73,6 +73,8 @@ int vqvs_device_info(int* cc, int* sm_count);
  * Valid when every consuming GroupNorm group is a union of whole G-granules of this tensor. */
 #define VQVS_CONV_STAT_GRAN_SHIFT 12
 
+struct VqvsGnFinalize; /* defined below */
+
 typedef struct VqvsConv {
   int32_t batch;
   int32_t c_a, c_b;        /* channels of xa and xb (c_b = 0: no concat) */
@@ -100,6 +102,10 @@ typedef struct VqvsConv {
   const void* w_packed;    /* tcgen05 operand image made by vqvs_pack_conv_weights (UMMA path) */
   float* out;              /* [batch, c_out, t_out] */
   double* stats_out;       /* [batch, c_out, 2] or NULL */
+  /* HOST pointer or NULL.  When set (UMMA path, act = 1) the kernel derives scale/shift for its input itself from
+   * the producers' statistics, exactly as vqvs_gn_finalize would (same fp64 formulas), so the separate finalize
+   * launch between two convs disappears; `scale` / `shift` are then ignored. */
+  const struct VqvsGnFinalize* gn;
 } VqvsConv;
 
 /* fp32 CUDA-core implementation (any shape). */

@@ -673,7 +673,7 @@ template <int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
-                 const Geo g) {
+                 const Geo g, const VqvsGnFinalize fin) {
   extern __shared__ __align__(128) uint8_t smem[];
   // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
@@ -773,10 +773,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       (void)nt;
       if (d.act && n != staged_n) {  // per-sample GroupNorm/FiLM affine
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
-        for (int i = xtid; i < c_in / 2; i += XFORM_WARPS * 32) {  // pair-major: {sc0, sc1, sh0, sh1}
-          const float2 sc = *reinterpret_cast<const float2*>(d.scale + (size_t)n * c_in + 2 * i);
-          const float2 sh = *reinterpret_cast<const float2*>(d.shift + (size_t)n * c_in + 2 * i);
-          reinterpret_cast<float4*>(s_ss)[i] = make_float4(sc.x, sc.y, sh.x, sh.y);
+        if (fin.groups > 0) {
+          // fused GroupNorm(+FiLM) finalize: the same fp64 formulas as gn_finalize_kernel, evaluated by the consumer
+          // for the sample it is about to read (one separate launch per conv saved)
+          const int cg = c_in / fin.groups;
+          for (int i = xtid; i < c_in / 2; i += XFORM_WARPS * 32) {
+            float sc2[2], sh2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 2 * i + e, grp = c / cg;
+              double s = 0.0, ss = 0.0;
+              for (int cc = grp * cg; cc < (grp + 1) * cg; ++cc) {
+                const double* st = cc < fin.c_a ? fin.stats_a + ((size_t)n * fin.c_a + cc) * 2
+                                                : fin.stats_b + ((size_t)n * fin.c_b + (cc - fin.c_a)) * 2;
+                s += __ldcg(st);
+                ss += __ldcg(st + 1);
+              }
+              const double cnt = (double)cg * (double)fin.count;
+              const double mean = s / cnt;
+              double var = ss / cnt - mean * mean;
+              var = var > 0.0 ? var : 0.0;
+              const double rstd = rsqrt(var + 1e-5);
+              double sc = rstd * (double)fin.gamma[c];
+              double sh = (double)fin.beta[c] - mean * sc;
+              if (fin.film) {
+                const double fa = (double)fin.film[(size_t)n * fin.film_stride + c];
+                const double fb = (double)fin.film[(size_t)n * fin.film_stride + c_in + c];
+                sc = sc * (1.0 + fa);
+                sh = sh * (1.0 + fa) + fb;
+              }
+              sc2[e] = (float)sc;
+              sh2[e] = (float)sh;
+            }
+            reinterpret_cast<float4*>(s_ss)[i] = make_float4(sc2[0], sc2[1], sh2[0], sh2[1]);
+          }
+        } else {
+          for (int i = xtid; i < c_in / 2; i += XFORM_WARPS * 32) {  // pair-major: {sc0, sc1, sh0, sh1}
+            const float2 sc = *reinterpret_cast<const float2*>(d.scale + (size_t)n * c_in + 2 * i);
+            const float2 sh = *reinterpret_cast<const float2*>(d.shift + (size_t)n * c_in + 2 * i);
+            reinterpret_cast<float4*>(s_ss)[i] = make_float4(sc.x, sc.y, sh.x, sh.y);
+          }
         }
         staged_n = n;
         asm volatile("bar.sync 1, %0;" ::"n"(XFORM_WARPS * 32));
@@ -1663,7 +1699,15 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   const int expect = d->resize == VQVS_RESIZE_DOWN2 ? d->t_in / 2 : d->resize == VQVS_RESIZE_UP2 ? d->t_in * 2 : d->t_in;
   VQVS_CHECK_ARG(d->t_in > 0 && d->t_out == expect && d->batch > 0, "conv(umma): bad lengths");
   VQVS_CHECK_ARG(d->xa && (d->c_b == 0 || d->xb) && d->out && d->w_packed, "conv(umma): null pointer");
-  VQVS_CHECK_ARG(!d->act || (d->scale && d->shift), "conv(umma): act=1 needs scale/shift");
+  VQVS_CHECK_ARG(!d->act || d->gn || (d->scale && d->shift), "conv(umma): act=1 needs scale/shift or a fused GroupNorm");
+  VqvsGnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  if (d->act && d->gn) {
+    fin = *d->gn;
+    VQVS_CHECK_ARG(fin.c_a == d->c_a && fin.c_b == d->c_b && fin.batch == d->batch, "conv(umma): fused GroupNorm shape mismatch");
+    VQVS_CHECK_ARG(fin.groups > 0 && (fin.c_a + fin.c_b) % fin.groups == 0 && fin.count > 0, "conv(umma): fused GroupNorm bad groups");
+    VQVS_CHECK_ARG(fin.stats_a && (fin.c_b == 0 || fin.stats_b) && fin.gamma && fin.beta, "conv(umma): fused GroupNorm null pointer");
+  }
   if (d->skip_mode != VQVS_SKIP_NONE) {
     VQVS_CHECK_ARG(d->sa && d->s_a > 0 && (d->s_b == 0 || d->sb), "conv(umma): skip sources missing");
     const int sexp = d->skip_resize == VQVS_RESIZE_DOWN2 ? d->t_skip / 2 : d->skip_resize == VQVS_RESIZE_UP2 ? d->t_skip * 2 : d->t_skip;
@@ -1703,9 +1747,9 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
   if (g.mt == 2)
-    umma::conv_umma_kernel<2><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
+    umma::conv_umma_kernel<2><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin);
   else
-    umma::conv_umma_kernel<1><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g);
+    umma::conv_umma_kernel<1><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin);
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }

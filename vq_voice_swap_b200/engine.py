@@ -247,7 +247,9 @@ def weights_for(net, blocks: Sequence, backend: str) -> Weights:
 # ---------------------------------------------------------------------------------------------
 # op emitters
 # ---------------------------------------------------------------------------------------------
-def _emit_gn(plan: Plan, srcs: List[Act], gn: torch.nn.GroupNorm, scale, shift, film_ptr=0, film_stride=0):
+def _emit_gn(plan: Plan, srcs: List[Act], gn: torch.nn.GroupNorm, scale, shift, film_ptr=0, film_stride=0,
+             standalone: bool = True):
+    """GroupNorm(+FiLM) finalize.  standalone=False only builds the descriptor (for a conv that fuses it)."""
     d = L.GnFinalize()
     d.batch = plan.batch
     d.c_a = srcs[0].c
@@ -265,12 +267,18 @@ def _emit_gn(plan: Plan, srcs: List[Act], gn: torch.nn.GroupNorm, scale, shift, 
         off += src.c
     d.film, d.film_stride = film_ptr, film_stride
     d.scale, d.shift = L.ptr(scale), L.ptr(shift)
-    plan.add(L.OP_GN_FINALIZE, d)
+    if standalone:
+        plan.add(L.OP_GN_FINALIZE, d)
+    else:
+        plan.keep.append(d)
+    return d
 
 
 def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, scale=None, shift=None,
                resize=L.RESIZE_NONE, skip_srcs: Optional[List[Act]] = None, skip_proj=None, skip_resize=L.RESIZE_NONE,
-               packed=None, name=None):
+               packed=None, name=None, norm=None):
+    """norm = (GroupNorm module, film_ptr, film_stride): the GroupNorm(+FiLM) in front of this conv.  On the tcgen05
+    path its finalize is fused into the conv kernel (VqvsConv.gn); otherwise a vqvs_gn_finalize op is emitted first."""
     d = L.Conv()
     d.batch = plan.batch
     d.c_a, d.c_b = srcs[0].c, (srcs[1].c if len(srcs) > 1 else 0)
@@ -298,6 +306,12 @@ def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, 
     kind = L.OP_CONV_SIMT
     if plan.backend == "umma" and packed is not None and L.load().vqvs_conv1d_umma_supported(C.byref(d)):
         kind = L.OP_CONV_UMMA
+    if norm is not None:
+        gn, film_ptr, film_stride = norm
+        fuse = kind == L.OP_CONV_UMMA and not os.environ.get("VQVS_NO_GN_FUSION")
+        fin = _emit_gn(plan, srcs, gn, scale, shift, film_ptr, film_stride, standalone=not fuse)
+        if fuse:
+            d.gn = C.addressof(fin)
     plan.add(kind, d, name)
     return kind
 
@@ -306,15 +320,14 @@ def _emit_block(plan: Plan, blk, srcs: List[Act], h1: Act, out: Act, w: Weights,
     """One reference ResBlock = GN finalize, fused conv1, GN(+FiLM) finalize, fused conv2(+skip)."""
     sc_a, sh_a, sc_b, sh_b = scratch
     mode = resize_mode(blk.scale_factor)
-    _emit_gn(plan, srcs, blk.pre_cond[0][0], sc_a, sh_a)
-    _emit_conv(plan, srcs, blk.pre_cond[2], h1, scale=sc_a, shift=sh_a, resize=mode, packed=w.packed.get((id(blk), 1)))
+    _emit_conv(plan, srcs, blk.pre_cond[2], h1, scale=sc_a, shift=sh_a, resize=mode, packed=w.packed.get((id(blk), 1)),
+               norm=(blk.pre_cond[0][0], 0, 0))
     film_ptr = film_stride = 0
     if getattr(blk, "emb_channels", None):
         film_ptr = ab.data_ptr() + 4 * w.film_offsets[id(blk)]
         film_stride = w.film_total
-    _emit_gn(plan, [h1], blk.pre_cond[3], sc_b, sh_b, film_ptr, film_stride)
     _emit_conv(plan, [h1], _tail_conv(blk), out, scale=sc_b, shift=sh_b, skip_srcs=srcs, skip_proj=_skip_proj(blk),
-               skip_resize=mode, packed=w.packed.get((id(blk), 2)))
+               skip_resize=mode, packed=w.packed.get((id(blk), 2)), norm=(blk.pre_cond[3], film_ptr, film_stride))
 
 
 class _Alloc:

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 RESIZE_NONE, RESIZE_DOWN2, RESIZE_UP2 = 0, 1, 2
 SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
@@ -29,6 +29,7 @@ class Conv(C.Structure):
         ("s_a", _i32), ("s_b", _i32), ("t_skip", _i32), ("skip_resize", _i32), ("reserved_", _i32),
         ("xa", _p), ("xb", _p), ("scale", _p), ("shift", _p), ("w", _p), ("bias", _p),
         ("sa", _p), ("sb", _p), ("w_skip", _p), ("b_skip", _p), ("w_packed", _p), ("out", _p), ("stats_out", _p),
+        ("gn", _p),
     ]
 
 
