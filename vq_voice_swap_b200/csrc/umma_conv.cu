@@ -21,6 +21,7 @@
 // The optional 1x1 skip conv (reference models/unet.py:265-271) is extra K blocks over the raw input.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -82,7 +83,8 @@ struct Geo {
 __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g) {
+static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g,
+                     int prefer_mt = 0) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
   g->n_tiles = (c_out + 255) / 256;
   if (c_out % g->n_tiles) return false;
@@ -142,6 +144,8 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->off_raw = off;
   const int left0 = budget - off;
   bool ok = false;
+  static const int force_mt = getenv("VQVS_FORCE_MT") ? atoi(getenv("VQVS_FORCE_MT")) : 0;
+  static const int force_kbs = getenv("VQVS_FORCE_KBS") ? atoi(getenv("VQVS_FORCE_KBS")) : 0;
   // stage sizes must be 1, 2 or 4 K blocks (the transform warps split a stage by powers of two)
   auto sizes_ok = [](int nkb, int kbs) { return nkb == 0 || kbs < 4 || (nkb % 4) != 3; };
   for (int cand = 0; cand < 6 && !ok; ++cand) {
@@ -149,6 +153,9 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     const int mt = (!g->w_resident && cand < 3) ? 2 : 1;
     const int kbs = 4 >> (cand % 3);
     if (g->w_resident && cand < 3) continue;
+    if (force_mt && mt != force_mt && !g->w_resident) continue;   // tuning aids (VQVS_FORCE_MT / VQVS_FORCE_KBS)
+    if (!force_mt && prefer_mt && mt != prefer_mt && !g->w_resident) continue;
+    if (force_kbs && kbs != force_kbs) continue;
     if (!sizes_ok(g->nkb_main, kbs) || !sizes_ok(g->nkb_skip, kbs)) continue;
     if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;
     const int ab_slot = kbs * (mt * g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
@@ -370,6 +377,11 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
@@ -1138,7 +1150,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       };
       const int row = quarter * 32 + lane;
       const int skip_shift = d.skip_resize == VQVS_RESIZE_UP2 ? 1 : 0;
-      const bool stack = g.stack != 0;
+      constexpr bool stack = NCH == 1;  // a 64-channel N tile is always stacked (make_geo), wider ones never
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         TILE_COORDS(tile)
@@ -1236,17 +1248,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 mbar_arrive(ACC_EMPTY(buf));
               }
               if (t_ok && !(d.reserved_ & 16)) {
-                const float* bias = s_bias + c0;
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+                const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
                 float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float o = __uint_as_float(vr[i]) + bias[i];
-                  if (stack) o += __uint_as_float(wr[i]);
-                  if (SKIPK != 0) o += sk[i];
-                  outp[(size_t)i * d.t_out] = o;
-                  v[i] = o;
+                for (int i = 0; i < 4; ++i) {  // packed fp32x2 adds: accumulator (+ lo half) + bias (+ skip)
+                  uint64_t o = add2(pack2(__uint_as_float(vr[2 * i]), __uint_as_float(vr[2 * i + 1])), pack2(bias[2 * i], bias[2 * i + 1]));
+                  if (stack) o = add2(o, pack2(__uint_as_float(wr[2 * i]), __uint_as_float(wr[2 * i + 1])));
+                  if (SKIPK != 0) o = add2(o, pack2(sk[2 * i], sk[2 * i + 1]));
+                  unpack2(o, v[2 * i], v[2 * i + 1]);
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) outp[(size_t)i * d.t_out] = v[i];
                 if (stats && !(d.reserved_ & 128)) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -1611,8 +1625,31 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
   if (c_skip && (d->s_a % umma::KBLK || d->s_b % umma::KBLK)) return 0;
   if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // paired loads need even rows
   const bool tma = tma_eligible(d);
-  if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g)) return 1;
-  return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g) ? 1 : 0;
+  auto geo = [&](int prefer_mt) {
+    if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g, prefer_mt))
+      return true;
+    return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g, prefer_mt);
+  };
+  if (!geo(0)) return 0;
+  if (g->mt == 2 && d->batch > 0 && d->t_out > 0) {
+    // Two time tiles per work item halve the weight streaming, but (measured, tools/prof_roles.py with VQVS_FORCE_MT)
+    // single tiles win when the epilogue also fetches an identity skip, and when the coarser items waste >= 10 % of
+    // the last round of the persistent schedule.
+    static int sms = 0;
+    if (!sms) {
+      int cc = 0;
+      if (vqvs_device_info(&cc, &sms) != VQVS_OK || sms <= 0) sms = 148;
+    }
+    const long long per = (long long)g->n_tiles * d->batch;
+    const long long items2 = per * ceil_div(d->t_out, 2 * umma::TILE_M), items1 = per * ceil_div(d->t_out, umma::TILE_M);
+    const long long rounds2 = 2 * ((items2 + sms - 1) / sms), rounds1 = (items1 + sms - 1) / sms;
+    const bool want1 = d->skip_mode == VQVS_SKIP_IDENTITY || 10 * rounds1 <= 9 * rounds2;
+    if (want1) {
+      Geo g2 = *g;
+      if (!geo(1)) *g = g2;  // keep the two-tile plan if a one-tile plan does not fit
+    }
+  }
+  return 1;
 }
 
 extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
