@@ -557,9 +557,60 @@ __device__ __forceinline__ void load_row8(const StageView& v, const float* raw_c
   }
 }
 
-// The row loop is deliberately NOT unrolled and every mode is a template parameter: the persistent CTA runs four
-// different role loops at once, and ncu showed instruction-fetch stalls (34 % of all warp samples) as the top stall
-// reason when these loops were unrolled into tens of KB of code.
+template <bool DOWN, bool ACT, int R>
+__device__ __forceinline__ void transform_row_group(const StageView& v, const float* raw_c, uint8_t* a_hi, uint8_t* a_lo,
+                                                    const uint64_t* sc, const uint64_t* sh, int row0) {
+  // R rows (32 apart) in flight at once: phase-major source order lets the scheduler interleave the GELU chains
+  float x[R][8], w[R][8];
+  uint64_t y[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r) load_row8<DOWN>(v, raw_c, v.tcs + row0 + 32 * r, x[r], w[r]);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[r][i] = pack2(x[r][2 * i], x[r][2 * i + 1]);
+  if (ACT) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[r][i] = fma2(y[r][i], sc[i], sh[i]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) gelu4p(y[r]);
+  }
+  if (DOWN) {
+    uint64_t z[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[r][i] = pack2(w[r][2 * i], w[r][2 * i + 1]);
+    if (ACT) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[r][i] = fma2(z[r][i], sc[i], sh[i]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) gelu4p(z[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[r][i] = fma2(y[r][i], bcast2(0.5f), mul2(z[r][i], bcast2(0.5f)));
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + 32 * r, tc = v.tcs + row;
+    uint4 hi, lo;
+    split4p(y[r], &hi, &lo);
+    // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
+    if (tc < 0 || tc >= v.t_conv) hi = lo = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
+    *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+  }
+}
+
+// The row loop is deliberately NOT unrolled beyond two rows and every mode is a template parameter: the persistent
+// CTA runs four different role loops at once, and ncu showed instruction-fetch stalls (34 % of all warp samples) as
+// the top stall reason when these loops were unrolled into tens of KB of code.
 template <bool DOWN, bool ACT>
 __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
                                                int chunk, int row_first, int nit) {
@@ -575,39 +626,13 @@ __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t
   const float* raw_c = reinterpret_cast<const float*>(raw_kb) + (chunk * 8) * v.box_w;
   uint8_t* a_hi = a_kb + chunk * (v.rows * 16);
   uint8_t* a_lo = a_hi + v.rows * 32;
+  int it = 0;
+  if (!DOWN) {  // (pooled rows already run two GELU batches per row)
 #pragma unroll 1
-  for (int it = 0; it < nit; ++it) {
-    const int row = row_first + 32 * it;
-    const int tc = v.tcs + row;
-    float x[8], w[8];
-    // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
-    load_row8<DOWN>(v, raw_c, tc, x, w);
-    uint64_t y[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] = pack2(x[2 * i], x[2 * i + 1]);
-    if (ACT) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = fma2(y[i], sc[i], sh[i]);
-      gelu4p(y);
-    }
-    if (DOWN) {
-      uint64_t z[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) z[i] = pack2(w[2 * i], w[2 * i + 1]);
-      if (ACT) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) z[i] = fma2(z[i], sc[i], sh[i]);
-        gelu4p(z);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = fma2(y[i], bcast2(0.5f), mul2(z[i], bcast2(0.5f)));
-    }
-    uint4 hi, lo;
-    split4p(y, &hi, &lo);
-    if (tc < 0 || tc >= v.t_conv) hi = lo = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
-    *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+    for (; it + 2 <= nit; it += 2) transform_row_group<DOWN, ACT, 2>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
   }
+#pragma unroll 1
+  for (; it < nit; ++it) transform_row_group<DOWN, ACT, 1>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
 }
 
 template <bool DOWN>
