@@ -328,6 +328,40 @@ def test_cpu_tensors_fail_loudly():
 # ---------------------------------------------------------------------------
 # BASELINE sizes: unet64, 64000-sample waveforms
 # ---------------------------------------------------------------------------
+WIDE_CASES = {
+    # name: (channels, out_channels, T, scale_factor, dilation, batch) -- shapes that exercise the wide N tiles (128 / 256
+    # columns, statistics granularity 4 / 8 / 16), streamed weights with one and two time tiles per item, ragged last
+    # tiles and the non-TMA direct mode (T % 4 != 0)
+    "c128_plain": (128, 128, 1000, 1.0, 2, 3),
+    "c128_widen": (128, 256, 520, 1.0, 2, 2),
+    "c256_direct": (256, 256, 333, 1.0, 2, 2),
+    "c512_dil8": (512, 512, 250, 1.0, 8, 2),
+    "c128_down": (128, 128, 2056, 0.5, 2, 2),
+    "c128_up": (128, 128, 516, 2.0, 2, 2),
+    "c192_narrow": (192, 64, 4100, 1.0, 2, 2),
+    "c64_long_ragged": (64, 64, 12345 * 4, 1.0, 2, 5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WIDE_CASES))
+def test_resblock_wide_vs_oracle(name, monkeypatch):
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    from vq_voice_swap_b200.unet import ResBlock
+
+    c, co, t, sf, dil, batch = WIDE_CASES[name]
+    blk = ResBlock(c, 256, co, scale_factor=sf, dilation=dil)
+    sd = synth.synth_state_dict(synth.shapes_of(blk), tag=f"wide/{name}")
+    blk.load_state_dict(sd)
+    x = synth.normal(f"wide/{name}/x", (batch, c, t))
+    emb = synth.normal(f"wide/{name}/emb", (batch, 256))
+    ref = O.resblock(x, emb, sd, "", scale_factor=sf, dilation=dil)
+    got = blk.to(DEV)(x.to(DEV), emb.to(DEV)).cpu()
+    assert rel_l2(got, ref) <= 1e-4
+    # a second call on the same plan (statistics arena re-zeroed, weights resident) must give the same answer
+    again = blk(x.to(DEV), emb.to(DEV)).cpu()
+    assert rel_l2(again, got) <= 1e-6
+
+
 @pytest.fixture(scope="module")
 def unet64():
     from vq_voice_swap_b200.diffusion_model import DiffusionModel
