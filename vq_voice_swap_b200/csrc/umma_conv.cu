@@ -139,7 +139,8 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   off = align_up(off, 128);
   g->off_w = off;
   const long long w_img = g->per_tile_bytes;
-  g->w_resident = (g->n_tiles == 1 && w_img <= 100 * 1024) ? 1 : 0;
+  static const int resident_kb = getenv("VQVS_RESIDENT_KB") ? atoi(getenv("VQVS_RESIDENT_KB")) : 150;  // tuning aid (147 KB: the 192 -> 64 concat convs)
+  g->w_resident = (g->n_tiles == 1 && w_img <= (long long)resident_kb * 1024) ? 1 : 0;
   if (g->w_resident) off += (int)w_img;
   g->off_raw = off;
   const int left0 = budget - off;
@@ -160,7 +161,7 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;
     const int ab_slot = kbs * (mt * g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
     const int raw_slot = mt * kbs * g->raw_kb_bytes;
-    const int min_ab = 2, min_raw = tma ? (kbs == 4 ? 2 : 3) : 0;
+    const int min_ab = 2, min_raw = tma ? ((kbs == 4 || w_img > 100 * 1024) ? 2 : 3) : 0;
     if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
     if (kbs >= 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
     int ab = MAX_AB_SLOTS;
