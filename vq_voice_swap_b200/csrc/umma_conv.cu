@@ -55,6 +55,7 @@ struct Geo {
   int nkb_main, nkb_skip;   // K blocks (16 channels) of the main taps / of the 1x1 skip
   int pad, rows;            // halo and operand rows (= 128 + 2*pad)
   int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
+  int epi_fast, epi_nch, epi_na;  // register-statistics epilogue: eligible / 32-column chunks per warp / accumulators per chunk
   int stack;                // 1: weight rows are [W_hi ; W_lo] (N = 2*n_tile): two MMAs per tap give all four
                             //    hi/lo products, the epilogue adds the two column halves
   int a_kb_bytes;           // operand bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
@@ -707,7 +708,10 @@ struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division
   }
 };
 
-template <int MT>
+// LEAN = the common case (TMA staging + register-statistics epilogue) compiled WITHOUT the generic paths (direct
+// global loads, per-tile butterfly epilogue): carrying unused code costs registers in the role loops (an unused
+// 470-line experiment slowed this kernel by 10 %), so the hot instantiation contains only what it runs.
+template <int MT, bool LEAN>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
@@ -865,7 +869,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         uint8_t* a_slot0 = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
-        if (g.tma) {
+        if (LEAN || g.tma) {
           mbar_wait(RAW_FULL(rw.idx), rw.ph);
           PROF_ADD(1, tprev);
           StageView v = is_skip ? vs : vm;
@@ -911,7 +915,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               }
             }
           }
-        } else {
+        } else if constexpr (!LEAN) {
          for (int j = 0; j < MT; ++j) {
           uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
           const int t0j = t0 + j * TILE_M;
@@ -1135,13 +1139,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     // per-tile transposing butterfly) and reduces across the warp's 32 rows only when the sample changes or
     // every STAT_FLUSH_TILES tiles (keeps the fp32 partial sums short), then one fp64 atomic per pair.
     // statistics granularity G granted by the caller (1 = per channel): NA = 32 / G accumulators per 32-column chunk
-    const int gran_log2 = !(d.reserved_ & VQVS_CONV_PAIR_STATS) ? 0 : max(1, (d.reserved_ >> VQVS_CONV_STAT_GRAN_SHIFT) & 15);
-    const int nch = n_chunks32 / EPI_SPLIT;  // 32-column chunks per epilogue warp
-    // accumulators per chunk and kind: as few as the granularity allows, at most 32 registers per kind in total
-    const int na = !stats ? 4 : nch == 1 ? 16 : nch == 2 ? (gran_log2 >= 2 ? 8 : 16) : (gran_log2 >= 3 ? 4 : 8);
-    const bool gran_ok = !stats || (gran_log2 >= 1 && (32 >> gran_log2) <= na);
-    const bool fast = gran_ok && !tail16 && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * EPI_SPLIT &&
-                      !(d.reserved_ & 32);
+    // (eligibility and the accumulator plan are decided on the host: epilogue_plan())
+    const int nch = g.epi_nch, na = g.epi_na;
+    const bool fast = LEAN || g.epi_fast;
     auto run_fast = [&](auto nch_c, auto na_c, auto skipk_c) {
       constexpr int NCH = decltype(nch_c)::value;
       constexpr int NA = decltype(na_c)::value;        // statistics accumulators per 32-column chunk (granularity 32 / NA)
@@ -1322,7 +1322,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       else if (nch == 2) dispatch_skip(I2{}, I8{});
       else if (na == 8) dispatch_skip(I4{}, I8{});
       else dispatch_skip(I4{}, I4{});
-    } else {
+    } else if constexpr (!LEAN) {
     auto flush_stats = [&](int fn, int fnt) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -1781,8 +1781,10 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1809,10 +1811,28 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;
   g.tiles_per_cta = ceil_div(g.tiles_total, grid);  // round-robin schedule: every SM gets a CTA
-  if (g.mt == 2)
-    umma::conv_umma_kernel<2><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin);
-  else
-    umma::conv_umma_kernel<1><<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin);
+  {  // epilogue plan (mirrors the role code): statistics granularity G granted by the caller -> accumulators per chunk
+    const int n_chunks32 = g.n_tile / 32, nch = n_chunks32 / umma::EPI_SPLIT;
+    const bool stats = d->stats_out != nullptr && !(d->reserved_ & 1);
+    const int gran_log2 = !(d->reserved_ & VQVS_CONV_PAIR_STATS) ? 0 : ((d->reserved_ >> VQVS_CONV_STAT_GRAN_SHIFT) & 15) > 1
+                                                                        ? ((d->reserved_ >> VQVS_CONV_STAT_GRAN_SHIFT) & 15) : 1;
+    // as few accumulators as the granularity allows, at most 32 registers per kind in total
+    const int na = !stats ? 4 : nch == 1 ? 16 : nch == 2 ? (gran_log2 >= 2 ? 8 : 16) : (gran_log2 >= 3 ? 4 : 8);
+    const bool gran_ok = !stats || (gran_log2 >= 1 && (32 >> gran_log2) <= na);
+    g.epi_nch = nch;
+    g.epi_na = na;
+    g.epi_fast = gran_ok && !(g.n_tile & 31) && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * umma::EPI_SPLIT &&
+                 !(d->reserved_ & 32);
+  }
+  const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 512);
+  auto launch = [&](auto kern) { kern<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin); };
+  if (g.mt == 2) {
+    if (lean) launch(umma::conv_umma_kernel<2, true>);
+    else launch(umma::conv_umma_kernel<2, false>);
+  } else {
+    if (lean) launch(umma::conv_umma_kernel<1, true>);
+    else launch(umma::conv_umma_kernel<1, false>);
+  }
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }
