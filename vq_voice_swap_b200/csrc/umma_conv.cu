@@ -731,6 +731,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   float2* s_ss = reinterpret_cast<float2*>(smem + g.off_ss);    // (scale, shift) of the current sample
   float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
   const int c_in = d.c_a + d.c_b;
+  const int dbg_flags = LEAN ? 0 : d.reserved_;  // profiling / ablation switches exist only in the generic instantiation
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches are uniform and the
   // MMA / TMA warps can keep their loop state and descriptors in uniform registers (no R2UR per tcgen05.mma)
@@ -796,7 +797,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
-    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && xtid == 32);
+    PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && xtid == 32);
     // per-CTA constants of the two operand sources (main taps / 1x1 skip)
     StageView vm, vs;
     vm.rows = vs.rows = g.rows;
@@ -806,7 +807,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     vm.t_src = d.t_in;        vs.t_src = d.t_skip;
     vm.t_conv = vs.t_conv = d.t_out;
     vm.resize = d.resize;     vs.resize = d.skip_resize;
-    vm.act = d.act && !(d.reserved_ & 8);
+    vm.act = d.act && !(dbg_flags & 8);
     vs.act = false;
     const int main_step = (TILE_M * g.main_origin_mul) / 2, skip_step = (TILE_M * g.skip_origin_mul) / 2;
     TILE_ITER_INIT();
@@ -886,7 +887,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           for (int j = 0; j < MT; ++j, v.x0 += step, v.tcs += TILE_M) {  // the time tiles of this item share the stage's weights
             const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes + j * g.kbs * g.raw_kb_bytes;
             uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
-            if (d.reserved_ & 64) {
+            if (dbg_flags & 64) {
               // ablation: no staging work at all
             } else if (v.resize == VQVS_RESIZE_UP2) {
               const int first = v.tcs >> 1;
@@ -1049,7 +1050,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const uint32_t a_kb16 = g.a_kb_bytes >> 4;
     if (g.w_resident) mbar_wait(W_FULL, 0);
     Ring ab(g.ab_slots);
-    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && lane == 0);
+    PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && lane == 0);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
       const int buf = k_local % g.nbuf;
       PROF_ADD(3, tprev);
@@ -1079,7 +1080,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         // built every descriptor in vector registers and moved it over with R2UR: ~100+ cycles of scalar work per MMA,
         // twice the 67 cycles the tensor pipe needs -- tools/mma_bench.cu.)
         const bool issue = elect_one();
-        const bool do_mma = !(d.reserved_ & 4);
+        const bool do_mma = !(dbg_flags & 4);
         uint64_t da_j = a_const + a16;
         const uint64_t db_0 = b_const + b16;
         const uint32_t a_step_j = g.kbs * a_kb16;
@@ -1129,10 +1130,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     int staged_nt = -1, stat_n = -1, stat_nt = 0;
     // running per-channel (sum, sumsq) of this warp's rows for up to 4 chunks, flushed when the sample changes
     double rs1[2] = {0, 0}, rs2[2] = {0, 0};
-    PROF_DECL((d.reserved_ & 512) && blockIdx.x == 0 && etid == 0);
+    PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && etid == 0);
     const int n_chunks32 = g.n_tile / 32;
     const bool tail16 = (g.n_tile & 31) != 0;
-    const bool stats = d.stats_out && !(d.reserved_ & 1);
+    const bool stats = d.stats_out && !(dbg_flags & 1);
     // ---- fast path: N tile of 64 or 128 channels, statistics kept in registers across the CTA's tiles ----
     // Each thread owns one row (time position) of the tile and NCH x 32 channel columns; it accumulates
     // (sum, sumsq) per channel PAIR in fp32 registers (2 instructions per element instead of the ~8 of a
@@ -1169,7 +1170,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const float r = column_sums32(arr, lane);  // lane l: l < NA -> sum of granule l, l < 2 NA -> sumsq of granule l - NA
           const int gi = lane < NA ? lane : lane - NA;
           const int co = fnt * g.n_tile + (half + EPI_SPLIT * c) * 32 + (gi << GSH);
-          if (lane < 2 * NA && !(d.reserved_ & 2))
+          if (lane < 2 * NA && !(dbg_flags & 2))
             atomicAdd(d.stats_out + ((size_t)fn * d.c_out + co) * 2 + (lane < NA ? 0 : 1), (double)r);
         }
         since_flush = 0;
@@ -1273,7 +1274,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(buf));
               }
-              if (t_ok && !(d.reserved_ & 16)) {
+              if (t_ok && !(dbg_flags & 16)) {
                 const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
                 const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
@@ -1287,7 +1288,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) outp[(size_t)i * d.t_out] = v[i];
-                if (stats && !(d.reserved_ & 128)) {
+                if (stats && !(dbg_flags & 128)) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     s1[c][(sub * 8 + i) >> GSH] += v[i];
@@ -1371,7 +1372,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 #pragma unroll 1
       for (int ci = 0; ci < 8 / EPI_SPLIT; ++ci) {
         const int ch = half + EPI_SPLIT * ci;
-        if (ch >= n_chunks32 || (d.reserved_ & 16)) break;
+        if (ch >= n_chunks32 || (dbg_flags & 16)) break;
         const int co0 = nt * g.n_tile + ch * 32;
         // identity-skip operands are fetched BEFORE waiting for the accumulator (latency overlaps the MMAs)
         float sk[32], sk_lo[32];
@@ -1459,7 +1460,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         if (do_tail) tmem_ld16(acc_addr + cbase, v);  // (stacking is never combined with a 16-column tail)
         tc_fence_before();
         mbar_arrive(ACC_EMPTY(buf));
-        if (do_tail && !(d.reserved_ & 16)) {
+        if (do_tail && !(dbg_flags & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = nt * g.n_tile + cbase + j;
@@ -1824,7 +1825,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     g.epi_fast = gran_ok && !(g.n_tile & 31) && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * umma::EPI_SPLIT &&
                  !(d->reserved_ & 32);
   }
-  const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 512);
+  const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
   auto launch = [&](auto kern) { kern<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin); };
   if (g.mt == 2) {
     if (lean) launch(umma::conv_umma_kernel<2, true>);
