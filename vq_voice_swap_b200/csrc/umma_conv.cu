@@ -711,11 +711,14 @@ struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division
 // LEAN = the common case (TMA staging + register-statistics epilogue) compiled WITHOUT the generic paths (direct
 // global loads, per-tile butterfly epilogue): carrying unused code costs registers in the role loops (an unused
 // 470-line experiment slowed this kernel by 10 %), so the hot instantiation contains only what it runs.
-template <int MT, bool LEAN>
+// KIND 0 = generic, 1 = LEAN, 2 = LEAN and PLAIN (no pooling / upsampling in the staged operands: 114 of the 130 convs
+// of a UNet step), which also drops the resampling transforms.
+template <int MT, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g, const VqvsGnFinalize fin) {
+  constexpr bool LEAN = KIND != 0, PLAIN = KIND == 2;
   extern __shared__ __align__(128) uint8_t smem[];
   // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
@@ -889,7 +892,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
             if (dbg_flags & 64) {
               // ablation: no staging work at all
-            } else if (v.resize == VQVS_RESIZE_UP2) {
+            } else if (!PLAIN && v.resize == VQVS_RESIZE_UP2) {
               const int first = v.tcs >> 1;
               const int nsrc = ((v.tcs + v.n_rows - 1) >> 1) - first + 1;
               for (int i = xtid; i < nk * 2 * nsrc; i += XFORM_WARPS * 32) {
@@ -897,7 +900,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 transform_up2(v, raw + (qq >> 1) * g.raw_kb_bytes, a_slot + (qq >> 1) * g.a_kb_bytes, ss + (qq >> 1) * KBLK, qq & 1, first + jj);
               }
             } else {
-              const bool down = v.resize == VQVS_RESIZE_DOWN2;
+              const bool down = !PLAIN && v.resize == VQVS_RESIZE_DOWN2;
               if constexpr (!HALO) {
                 const uint8_t* raw_q = raw + (q >> 1) * g.raw_kb_bytes;
                 uint8_t* a_q = a_slot + (q >> 1) * g.a_kb_bytes;
@@ -1782,10 +1785,11 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma::conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma::conv_umma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    auto allow = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
+    allow(umma::conv_umma_kernel<1, 0>); allow(umma::conv_umma_kernel<2, 0>);
+    allow(umma::conv_umma_kernel<1, 1>); allow(umma::conv_umma_kernel<2, 1>);
+    allow(umma::conv_umma_kernel<1, 2>); allow(umma::conv_umma_kernel<2, 2>);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1827,12 +1831,16 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
   auto launch = [&](auto kern) { kern<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin); };
+  const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE);
+  const int kind = !lean ? 0 : plain ? 2 : 1;
   if (g.mt == 2) {
-    if (lean) launch(umma::conv_umma_kernel<2, true>);
-    else launch(umma::conv_umma_kernel<2, false>);
+    if (kind == 2) launch(umma::conv_umma_kernel<2, 2>);
+    else if (kind == 1) launch(umma::conv_umma_kernel<2, 1>);
+    else launch(umma::conv_umma_kernel<2, 0>);
   } else {
-    if (lean) launch(umma::conv_umma_kernel<1, true>);
-    else launch(umma::conv_umma_kernel<1, false>);
+    if (kind == 2) launch(umma::conv_umma_kernel<1, 2>);
+    else if (kind == 1) launch(umma::conv_umma_kernel<1, 1>);
+    else launch(umma::conv_umma_kernel<1, 0>);
   }
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
