@@ -685,7 +685,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Optional role profiler (debug flag 512): cycles per phase of block 0, read back with vqvs_debug_prof.
-__device__ unsigned long long g_prof[32];
+static __device__ unsigned long long g_prof[32];  // (one copy per translation unit; only the generic kernels' unit writes it)
 #ifdef VQVS_PROF
 #define PROF_ADD(slot, since) do { if (prof) { const long long now_ = clock64(); acc_[slot] += now_ - (since); (since) = now_; } } while (0)
 #define PROF_DECL(cond) const bool prof = (cond); long long acc_[4] = {0, 0, 0, 0}; long long tprev = prof ? clock64() : 0
@@ -718,7 +718,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                  const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g, const VqvsGnFinalize fin) {
-  constexpr bool LEAN = KIND != 0, PLAIN = KIND == 2;
+  // KIND 3 = PLAIN and additionally no 1x1-skip stages and resident weights (conv1 and identity-skip conv2 of every
+  // 64-channel layer: the largest share of a step)
+  constexpr bool LEAN = KIND != 0, PLAIN = KIND >= 2, SIMPLE = KIND == 3;
   extern __shared__ __align__(128) uint8_t smem[];
   // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
@@ -869,7 +871,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         PROF_ADD(3, tprev);
         mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
         PROF_ADD(0, tprev);
-        const bool is_skip = st >= g.main_stages;
+        const bool is_skip = !SIMPLE && st >= g.main_stages;
         const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         uint8_t* a_slot0 = smem + g.off_ab + ab.idx * g.ab_slot_bytes;
@@ -967,7 +969,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int x0m = (t0 * g.main_origin_mul) / 2 + g.main_origin_off;
         const int x0s = (t0 * g.skip_origin_mul) / 2;
         for (int st = 0; st < total_stages; ++st) {
-          const bool is_skip = st >= g.main_stages;
+          const bool is_skip = !SIMPLE && st >= g.main_stages;
           const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
           const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
           mbar_wait(RAW_EMPTY(rw.idx), rw.ph ^ 1);
@@ -1008,7 +1010,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == TMA_W_WARP) {
     // =========================== TMA: weight image ===========================
-    if (g.w_resident) {  // loaded once, reused by every tile of this CTA
+    if (SIMPLE || g.w_resident) {  // loaded once, reused by every tile of this CTA
       if (elect_one()) {
         const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed);
         const uint32_t total = (uint32_t)g.per_tile_bytes;
@@ -1026,7 +1028,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int nt = it_nt;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
         for (int st = 0; st < total_stages; ++st) {
-          const bool is_skip = st >= g.main_stages;
+          const bool is_skip = !SIMPLE && st >= g.main_stages;
           const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
           const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
           const uint32_t bytes = nk * (is_skip ? g.b_unit_skip : g.b_unit_main);
@@ -1051,7 +1053,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
     const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
     const uint32_t a_kb16 = g.a_kb_bytes >> 4;
-    if (g.w_resident) mbar_wait(W_FULL, 0);
+    if (SIMPLE || g.w_resident) mbar_wait(W_FULL, 0);
     Ring ab(g.ab_slots);
     PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && lane == 0);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
@@ -1066,15 +1068,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       for (int st = 0; st < total_stages; ++st) {
         PROF_ADD(1, tprev);
         mbar_wait(A_FULL(ab.idx), ab.ph);
-        if (!g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
+        if (!SIMPLE && !g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
         tc_fence_after();
         PROF_ADD(0, tprev);
-        const bool is_skip = st >= g.main_stages;
+        const bool is_skip = !SIMPLE && st >= g.main_stages;
         const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
         const uint32_t unit16 = is_skip ? unit_skip16 : unit_main16;
-        const uint32_t b16 = g.w_resident ? w16 : a16 + MT * g.kbs * a_kb16;
+        const uint32_t b16 = (SIMPLE || g.w_resident) ? w16 : a16 + MT * g.kbs * a_kb16;
         w16 += nk * unit16;
         const int taps = is_skip ? 1 : d.ksize;
         const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
@@ -1516,6 +1518,50 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------
+// Translation units.  This file is compiled once per kernel KIND with -DVQVS_KIND_TU=<kind> (each unit instantiates only
+// that kind's kernels and exports one launcher) and once without (packer, self-test, C ABI): the instantiations
+// dominate the build time and compile in parallel this way (__graft_entry__.build()).
+// ---------------------------------------------------------------------------
+#define VQVS_LAUNCHER_ARGS int mt, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap* maps, const VqvsConv* d, \
+                           const Geo* g, const VqvsGnFinalize* fin
+cudaError_t launch_kind0(VQVS_LAUNCHER_ARGS);
+cudaError_t launch_kind1(VQVS_LAUNCHER_ARGS);
+cudaError_t launch_kind2(VQVS_LAUNCHER_ARGS);
+cudaError_t launch_kind3(VQVS_LAUNCHER_ARGS);
+cudaError_t read_prof(unsigned long long* host32);
+
+#ifdef VQVS_KIND_TU
+template <int KIND>
+static cudaError_t launch_kind_impl(VQVS_LAUNCHER_ARGS) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess && KIND != 3)
+      e = cudaFuncSetAttribute(conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (mt == 2 && KIND != 3)
+    conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND><<<grid, THREADS, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
+  else
+    conv_umma_kernel<1, KIND><<<grid, THREADS, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
+  return cudaGetLastError();
+}
+#if VQVS_KIND_TU == 0
+cudaError_t launch_kind0(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<0>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
+cudaError_t read_prof(unsigned long long* host32) { return cudaMemcpyFromSymbol(host32, g_prof, 32 * sizeof(unsigned long long)); }
+#elif VQVS_KIND_TU == 1
+cudaError_t launch_kind1(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<1>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
+#elif VQVS_KIND_TU == 2
+cudaError_t launch_kind2(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<2>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
+#else
+cudaError_t launch_kind3(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<3>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
+#endif
+}  // namespace umma
+}  // namespace vqvs
+#else  // main unit: packer, self-test, C ABI
+
+// ---------------------------------------------------------------------------
 // weight packer: fp32 [c_out, c_in, ksize] (+ [c_out, c_skip]) -> bf16 hi/lo smem image
 // ---------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ w_skip, int c_out, int c_in,
@@ -1783,20 +1829,6 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     if (d->skip_mode == VQVS_SKIP_IDENTITY)
       VQVS_CHECK_ARG(d->s_a + d->s_b == d->c_out, "conv(umma): identity skip channel mismatch");
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaSuccess;
-    auto allow = [&](auto kern) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
-    allow(umma::conv_umma_kernel<1, 0>); allow(umma::conv_umma_kernel<2, 0>);
-    allow(umma::conv_umma_kernel<1, 1>); allow(umma::conv_umma_kernel<2, 1>);
-    allow(umma::conv_umma_kernel<1, 2>); allow(umma::conv_umma_kernel<2, 2>);
-    if (e != cudaSuccess) {
-      (void)cudaGetLastError();
-      set_error("conv(umma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return VQVS_ECUDA;
-    }
-    attr_done = true;
-  }
   alignas(64) CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
   if (g.tma) {
@@ -1830,24 +1862,24 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
                  !(d->reserved_ & 32);
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
-  auto launch = [&](auto kern) { kern<<<grid, umma::THREADS, g.smem_bytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], *d, g, fin); };
   const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE);
-  const int kind = !lean ? 0 : plain ? 2 : 1;
-  if (g.mt == 2) {
-    if (kind == 2) launch(umma::conv_umma_kernel<2, 2>);
-    else if (kind == 1) launch(umma::conv_umma_kernel<2, 1>);
-    else launch(umma::conv_umma_kernel<2, 0>);
-  } else {
-    if (kind == 2) launch(umma::conv_umma_kernel<1, 2>);
-    else if (kind == 1) launch(umma::conv_umma_kernel<1, 1>);
-    else launch(umma::conv_umma_kernel<1, 0>);
+  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1;
+  const int kind = !lean ? 0 : simple ? 3 : plain ? 2 : 1;
+  cudaError_t le = kind == 3   ? umma::launch_kind3(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
+                   : kind == 2 ? umma::launch_kind2(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
+                   : kind == 1 ? umma::launch_kind1(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
+                               : umma::launch_kind0(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin);
+  if (le != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("vqvs_conv1d_umma: launch failed: %s", cudaGetErrorString(le));
+    return VQVS_ECUDA;
   }
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
   return VQVS_OK;
 }
 
 extern "C" int vqvs_debug_prof(unsigned long long* host32) {
-  cudaError_t e = cudaMemcpyFromSymbol(host32, umma::g_prof, 32 * sizeof(unsigned long long));
+  cudaError_t e = umma::read_prof(host32);
   if (e != cudaSuccess) {
     set_error("vqvs_debug_prof: %s", cudaGetErrorString(e));
     return VQVS_ECUDA;
@@ -1873,3 +1905,4 @@ extern "C" int vqvs_umma_selftest(const float* a, const float* b, float* dout, i
   VQVS_CHECK_LAUNCH("vqvs_umma_selftest");
   return VQVS_OK;
 }
+#endif  // VQVS_KIND_TU
