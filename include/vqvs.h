@@ -17,7 +17,9 @@
  *     a thread-local message for the last failure on the calling thread
  *   - per-channel statistics buffers are double[batch][channels][2] holding
  *     (sum, sum of squares) over time; producers ACCUMULATE into them with
- *     atomics, so the caller zeroes them once per forward (vqvs_run MEMSET op)
+ *     atomics, so the caller zeroes them once per forward (vqvs_run MEMSET op);
+ *     a producer granted a statistics granularity G (VQVS_CONV_STAT_GRAN_SHIFT)
+ *     adds the sums of G consecutive channels into the first channel's slot
  */
 #ifndef VQVS_H_
 #define VQVS_H_

@@ -2,23 +2,26 @@
 //
 //   D[t, co] = sum_{tap, ci} A_tap[t, ci] * W_tap[co, ci]      (M = 128 positions, N = co tile, K = ci)
 //
-// * A (activations) is produced IN-KERNEL: 256 producer threads read the raw fp32 input with
-//   coalesced loads, apply the fused prologue (GroupNorm/FiLM affine -> exact GELU -> pool /
-//   upsample / concat select), split every value into bf16 hi + bf16 lo and store it K-major,
-//   un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so the three
-//   conv taps are the SAME tile read through descriptors whose start address is shifted by
-//   tap*dilation rows -- the halo is staged once.
-// * W (weights) is pre-split into bf16 hi/lo and pre-arranged on the device into the exact smem
-//   image (vqvs_pack_conv_weights); one elected thread streams it with cp.async.bulk (TMA) onto an
-//   mbarrier.
-// * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), three MMAs per
-//   K block: hi*hi + lo*hi + hi*lo  ("bf16x3": ~2^-16 relative operand error, measured 1.5e-5 on a
-//   whole UNet forward vs 9.7e-4 for single TF32 -- tools/precision_study.py).
-// * Four epilogue warps read the (double-buffered) accumulator back with tcgen05.ld, add bias /
-//   identity skip, store coalesced along time, and reduce per-channel (sum, sumsq) for the next
-//   GroupNorm with a transposing shuffle butterfly, a shared-memory combine and fp64 atomics --
-//   while the transform/MMA warps already work on the CTA's next tile (persistent CTAs, one per SM).
+// One persistent CTA per SM (640 threads, 96 registers each), warp-specialised; every CTA owns a contiguous range of
+// work items (sample-major) of 1 or 2 tiles of 128 positions:
+// * TMA warp: raw fp32 activation boxes [16 channels x (128 + halo)] -> staging ring (zero fill outside the sequence).
+// * Weight warp: the operand image pre-split into bf16 hi/lo and pre-arranged by vqvs_pack_conv_weights, resident in
+//   shared memory for the whole CTA when it fits (<= 150 KB), else streamed per K block with cp.async.bulk.
+// * Transform warps (8 + 1 for the halo rows): optional GroupNorm(+FiLM) FINALIZE from the producers' statistics at every
+//   sample change, then per element affine -> exact-erf GELU (packed fp32x2) -> pool / upsample / concat select -> bf16
+//   hi + lo split, stored K-major, un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so
+//   the three conv taps are the SAME tile read through descriptors whose start address is shifted by tap*dilation rows --
+//   the halo is staged once.
+// * MMA warp: warp-uniform loop, elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM).  "bf16x3":
+//   hi*hi + lo*hi + hi*lo (~2^-16 relative operand error, measured 1.5e-5 on a whole UNet forward vs 9.7e-4 for single
+//   TF32 -- tools/precision_study.py); for 64-channel N tiles the weight rows are stacked [W_hi ; W_lo] (N = 128) so
+//   that two MMAs per tap give all four products.  Accumulators are double-buffered in TMEM.
+// * Epilogue warps (8): thread = time row.  tcgen05.ld -> + bias (+ lo half) (+ identity skip, prefetched) -> coalesced
+//   stores along time -> GroupNorm (sum, sumsq) of the OUTPUT accumulated in registers across the CTA's tiles, one
+//   accumulator per G-channel granule, reduced across lanes and flushed with fp64 atomics only when the sample changes.
 // The optional 1x1 skip conv (reference models/unet.py:265-271) is extra K blocks over the raw input.
+// The kernel exists in four KINDs (generic / LEAN / PLAIN / SIMPLE, see conv_umma_kernel) compiled as separate
+// translation units; measurements behind the design choices: tools/mma_bench.cu, tools/alu_bench.cu, profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
