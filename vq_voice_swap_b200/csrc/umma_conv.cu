@@ -51,6 +51,7 @@ constexpr int THREADS = (XFORM_WARP0 + XFORM_WARPS) * 32;
 constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
 constexpr int MAX_RAW_SLOTS = 16;
 constexpr int MAX_AB_SLOTS = 8;
+constexpr int SIMPLE_BOXW = 136;  // staging pitch of every un-resampled conv with dilation 1 or 2 (128 + 2 * 4)
 
 // Host-computed geometry shared by the packer and the kernel.
 struct Geo {
@@ -539,12 +540,13 @@ struct StageView {
 // chunk of ONE K block -> bf16 hi/lo operand rows.  The chunk's (scale, shift) are read once into registers as
 // packed pairs; the next row's raw values are fetched before the current row is evaluated.
 // raw / a point at the K block; ss at its 16 (scale, shift) pairs.
-template <bool DOWN>
+// BOXW != 0: the staging pitch is a compile-time constant (the channel offsets become immediates of the loads)
+template <bool DOWN, int BOXW = 0>
 __device__ __forceinline__ void load_row8(const StageView& v, const float* raw_c, int tc, float* x, float* w) {
   if (!DOWN) {
     const float* raw = raw_c + (tc - v.x0);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = raw[e * v.box_w];
+    for (int e = 0; e < 8; ++e) x[e] = raw[e * (BOXW ? BOXW : v.box_w)];
   } else {
     int col = 2 * tc - v.x0;
     const float* raw = raw_c;
@@ -562,14 +564,14 @@ __device__ __forceinline__ void load_row8(const StageView& v, const float* raw_c
   }
 }
 
-template <bool DOWN, bool ACT, int R>
+template <bool DOWN, bool ACT, int R, int BOXW = 0>
 __device__ __forceinline__ void transform_row_group(const StageView& v, const float* raw_c, uint8_t* a_hi, uint8_t* a_lo,
                                                     const uint64_t* sc, const uint64_t* sh, int row0) {
   // R rows (32 apart) in flight at once: phase-major source order lets the scheduler interleave the GELU chains
   float x[R][8], w[R][8];
   uint64_t y[R][4];
 #pragma unroll
-  for (int r = 0; r < R; ++r) load_row8<DOWN>(v, raw_c, v.tcs + row0 + 32 * r, x[r], w[r]);
+  for (int r = 0; r < R; ++r) load_row8<DOWN, BOXW>(v, raw_c, v.tcs + row0 + 32 * r, x[r], w[r]);
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -616,7 +618,7 @@ __device__ __forceinline__ void transform_row_group(const StageView& v, const fl
 // The row loop is deliberately NOT unrolled beyond two rows and every mode is a template parameter: the persistent
 // CTA runs four different role loops at once, and ncu showed instruction-fetch stalls (34 % of all warp samples) as
 // the top stall reason when these loops were unrolled into tens of KB of code.
-template <bool DOWN, bool ACT>
+template <bool DOWN, bool ACT, int BOXW = 0>
 __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
                                                int chunk, int row_first, int nit) {
   uint64_t sc[4], sh[4];
@@ -628,23 +630,23 @@ __device__ __forceinline__ void transform_rows(const StageView& v, const uint8_t
       sh[i] = pack2(p.z, p.w);
     }
   }
-  const float* raw_c = reinterpret_cast<const float*>(raw_kb) + (chunk * 8) * v.box_w;
+  const float* raw_c = reinterpret_cast<const float*>(raw_kb) + (chunk * 8) * (BOXW ? BOXW : v.box_w);
   uint8_t* a_hi = a_kb + chunk * (v.rows * 16);
   uint8_t* a_lo = a_hi + v.rows * 32;
   int it = 0;
   if (!DOWN) {  // (pooled rows already run two GELU batches per row)
 #pragma unroll 1
-    for (; it + 2 <= nit; it += 2) transform_row_group<DOWN, ACT, 2>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
+    for (; it + 2 <= nit; it += 2) transform_row_group<DOWN, ACT, 2, BOXW>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
   }
 #pragma unroll 1
-  for (; it < nit; ++it) transform_row_group<DOWN, ACT, 1>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
+  for (; it < nit; ++it) transform_row_group<DOWN, ACT, 1, BOXW>(v, raw_c, a_hi, a_lo, sc, sh, row_first + 32 * it);
 }
 
-template <bool DOWN>
+template <bool DOWN, int BOXW = 0>
 __device__ __forceinline__ void transform_rows_n(const StageView& v, const uint8_t* raw_kb, uint8_t* a_kb, const float2* ss_kb,
                                                  int chunk, int row_first, int nit) {
-  if (v.act) transform_rows<DOWN, true>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
-  else transform_rows<DOWN, false>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
+  if (v.act) transform_rows<DOWN, true, BOXW>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
+  else transform_rows<DOWN, false, BOXW>(v, raw_kb, a_kb, ss_kb, chunk, row_first, nit);
 }
 
 // nearest x2: one item = one SOURCE position of one K block -> two operand rows (GELU evaluated once)
@@ -911,7 +913,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 uint8_t* a_q = a_slot + (q >> 1) * g.a_kb_bytes;
                 const float2* ss_q = ss + (q >> 1) * KBLK;
                 if (down) transform_rows_n<true>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
-                else transform_rows_n<false>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
+                else transform_rows_n<false, SIMPLE ? SIMPLE_BOXW : 0>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
               } else {
                 const int n_extra = v.n_rows - TILE_M;
                 for (int i = lane; i < chunks * n_extra; i += 32) {
@@ -919,7 +921,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   const int row = TILE_M + (i - qq * n_extra);
                   const int k = qq >> 1;
                   if (down) transform_rows_n<true>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
-                  else transform_rows_n<false>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
+                  else transform_rows_n<false, SIMPLE ? SIMPLE_BOXW : 0>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
                 }
               }
             }
@@ -1866,7 +1868,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
   const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE);
-  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1;
+  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1 && g.main_box_w == umma::SIMPLE_BOXW;
   const int kind = !lean ? 0 : simple ? 3 : plain ? 2 : 1;
   cudaError_t le = kind == 3   ? umma::launch_kind3(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
                    : kind == 2 ? umma::launch_kind2(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
