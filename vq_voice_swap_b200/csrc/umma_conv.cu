@@ -913,7 +913,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 uint8_t* a_q = a_slot + (q >> 1) * g.a_kb_bytes;
                 const float2* ss_q = ss + (q >> 1) * KBLK;
                 if (down) transform_rows_n<true>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
-                else transform_rows_n<false, SIMPLE ? SIMPLE_BOXW : 0>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
+                else if (PLAIN && is_skip) transform_rows_n<false, PLAIN ? TILE_M : 0>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
+                else transform_rows_n<false, PLAIN ? SIMPLE_BOXW : 0>(v, raw_q, a_q, ss_q, q & 1, row_first, nk);
               } else {
                 const int n_extra = v.n_rows - TILE_M;
                 for (int i = lane; i < chunks * n_extra; i += 32) {
@@ -921,7 +922,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   const int row = TILE_M + (i - qq * n_extra);
                   const int k = qq >> 1;
                   if (down) transform_rows_n<true>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
-                  else transform_rows_n<false, SIMPLE ? SIMPLE_BOXW : 0>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
+                  else if (PLAIN && is_skip) transform_rows_n<false, PLAIN ? TILE_M : 0>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
+                  else transform_rows_n<false, PLAIN ? SIMPLE_BOXW : 0>(v, raw + k * g.raw_kb_bytes, a_slot + k * g.a_kb_bytes, ss + k * KBLK, qq & 1, row, 1);
                 }
               }
             }
@@ -1867,8 +1869,10 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
                  !(d->reserved_ & 32);
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
-  const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE);
-  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1 && g.main_box_w == umma::SIMPLE_BOXW;
+  // (PLAIN kinds compile the staging pitches in: 136 floats for the main taps at dilation 1 or 2, 128 for the 1x1 skip)
+  const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE) &&
+                     g.main_box_w == umma::SIMPLE_BOXW && (g.nkb_skip == 0 || g.skip_box_w == umma::TILE_M);
+  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1;
   const int kind = !lean ? 0 : simple ? 3 : plain ? 2 : 1;
   cudaError_t le = kind == 3   ? umma::launch_kind3(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
                    : kind == 2 ? umma::launch_kind2(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
