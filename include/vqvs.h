@@ -281,6 +281,10 @@ int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 /* Role profiler of the last vqvs_conv1d_umma launched with debug flag 512 (cycles per phase of CTA 0):
  * [0..3] transform warp 0: wait operand slot, wait raw, work, loop; [4..7] TMA; [8..11] MMA; [12..15] epilogue. */
 int vqvs_debug_prof(unsigned long long* host32);
+/* Shared-memory / pipeline plan vqvs_conv1d_umma would use for `d` (tuning aid and test hook, no launch):
+ * out16 = {n_tiles, n_tile, stack, w_resident, kbs, mt, nbuf, ab_slots, ab_slot_bytes, raw_slots, raw_slot_bytes,
+ *          smem_bytes, tma, main_stages, skip_stages, b_slots}. */
+int vqvs_debug_geo(const VqvsConv* d, int* out16);
 
 /* tcgen05 self-test: runs D[128,n] = A[128,k] * B[n,k]^T through the exact smem layout,
  * descriptors and TMEM read-back used by vqvs_conv1d_umma, with A rows shifted by `row_shift`.

@@ -48,8 +48,9 @@ constexpr int HALO_WARP = XFORM_WARP0;  // shares warpgroup 2 (small register bu
 constexpr int EPI_WARPS = 8;      // two warps per lane quarter split the column chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;  // warps sharing a TMEM lane quarter take alternate 32-column chunks
 constexpr int THREADS = (XFORM_WARP0 + XFORM_WARPS) * 32;
-constexpr int SMEM_HEADER = 512;  // 49 mbarriers + TMEM base holder
-constexpr int MAX_RAW_SLOTS = 16;
+constexpr int SMEM_HEADER = 512;  // 53 mbarriers + TMEM base holder
+constexpr int MAX_RAW_SLOTS = 8;
+constexpr int MAX_B_SLOTS = 8;
 constexpr int MAX_AB_SLOTS = 8;
 constexpr int SIMPLE_BOXW = 136;  // staging pitch of every un-resampled conv with dilation 1 or 2 (128 + 2 * 4)
 
@@ -73,7 +74,8 @@ struct Geo {
   int nbuf;                       // TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs)
   int raw_kb_bytes;               // raw staging bytes of ONE K block (a slot holds kbs of them)
   int raw_slot_bytes, raw_slots;  // fp32 staging ring filled by TMA (0 slots in direct mode)
-  int ab_slot_bytes, ab_slots;    // operand ring: kbs A tiles (+ the streamed weights of those K blocks)
+  int ab_slot_bytes, ab_slots;    // operand ring: the A tiles of one stage (mt * kbs K blocks)
+  int b_slot_bytes, b_slots, off_b;  // streamed weights: their own ring, ONE K block per slot (0 slots when resident)
   int main_stages, skip_stages;
   int w_resident;                 // 1: the whole weight image of the N tile stays in smem for all tiles of the CTA
   int smem_bytes;
@@ -164,18 +166,29 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     if (force_kbs && kbs != force_kbs) continue;
     if (!sizes_ok(g->nkb_main, kbs) || !sizes_ok(g->nkb_skip, kbs)) continue;
     if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;
-    const int ab_slot = kbs * (mt * g->a_kb_bytes + (g->w_resident ? 0 : g->b_unit_main));
+    // Streamed weights live in their own ring of single-K-block slots, so the A stage (kbs K blocks, shared by the mt time
+    // tiles) can be as large as the transform warps like: with the weights inside the operand slot every layer with
+    // C_out >= 128 ran one K block per stage, i.e. one row per transform thread per synchronisation (ncu: 29 instructions
+    // per element against 17 for the 4-K-block stages of the 64-channel layers).
+    const int ab_slot = kbs * mt * g->a_kb_bytes;
     const int raw_slot = mt * kbs * g->raw_kb_bytes;
+    const int b_slot = g->w_resident ? 0 : (g->b_unit_main > g->b_unit_skip ? g->b_unit_main : g->b_unit_skip);
     const int min_ab = 2, min_raw = tma ? ((kbs == 4 || w_img > 100 * 1024) ? 2 : 3) : 0;
-    if (left0 < min_ab * ab_slot + min_raw * raw_slot) continue;
-    if (kbs >= 2 && left0 < 3 * ab_slot + min_raw * raw_slot && !g->w_resident) continue;  // prefer 3 operand slots when streaming
+    int b_slots = 0;
+    if (!g->w_resident) {
+      b_slots = left0 - 3 * b_slot >= min_ab * ab_slot + min_raw * raw_slot ? 3 : 2;
+      if (kbs == 1 && left0 - 4 * b_slot >= 3 * ab_slot + (min_raw + 1) * raw_slot) b_slots = 4;
+    }
+    const int left = left0 - b_slots * b_slot;
+    if (left < min_ab * ab_slot + min_raw * raw_slot) continue;
     int ab = MAX_AB_SLOTS;
-    while (ab > min_ab && left0 - ab * ab_slot < (tma ? (kbs == 4 ? 3 : 4) * raw_slot : 0)) --ab;
-    if (left0 - ab * ab_slot < min_raw * raw_slot) continue;
+    while (ab > min_ab && left - ab * ab_slot < (tma ? (kbs == 4 ? 3 : 4) * raw_slot : 0)) --ab;
+    if (left - ab * ab_slot < min_raw * raw_slot) continue;
     if (ab > 4) ab = 4;
-    int raw = tma ? (left0 - ab * ab_slot) / raw_slot : 0;
+    int raw = tma ? (left - ab * ab_slot) / raw_slot : 0;
     if (raw > MAX_RAW_SLOTS) raw = MAX_RAW_SLOTS;
-    if (raw > 8) raw = 8;
+    g->b_slot_bytes = b_slot;
+    g->b_slots = b_slots;
     g->kbs = kbs;
     g->mt = mt;
     g->nbuf = (2 * mt * g->acc_cols <= 512) ? 2 : 1;
@@ -190,6 +203,8 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   off += g->raw_slots * g->raw_slot_bytes;
   g->off_ab = off;
   off += g->ab_slots * g->ab_slot_bytes;
+  g->off_b = off;
+  off += g->b_slots * g->b_slot_bytes;
   g->smem_bytes = off;
   g->main_stages = (g->nkb_main + g->kbs - 1) / g->kbs;
   g->skip_stages = (g->nkb_skip + g->kbs - 1) / g->kbs;
@@ -263,6 +278,51 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       "}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// ---- grouped MMA issue ---------------------------------------------------------------------------------------
+// All tcgen05.mma of ONE K block (k = 3: three taps) behind a single elected branch.  Descriptors travel as 32-bit low
+// words (start address + LBO; the callers advance them with warp-uniform 32-bit adds) plus one constant high word per
+// operand, and only the first product of an accumulator carries a runtime accumulate flag.  ncu (profiles/r2_*) showed
+// the issue loop itself -- ~17 instructions per MMA with a branch region, an R2UR and 64-bit adds for every tap -- to be
+// the limit of the 64-channel layers (134 cycles per N = 128 MMA against the 67 the tensor pipe needs).
+#define VQVS_MMA_(A, B, P) \
+  "mov.b64 da, {" A ", %1};\n\tmov.b64 db, {" B ", %2};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " P ";\n\t"
+#define VQVS_MMA_HEAD_ "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, %4, %4;\n\t"
+// stacked weight rows [W_hi ; W_lo]: (A_hi, A_lo) per tap
+__device__ __forceinline__ void mma_group_stack3(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                 uint32_t a0, uint32_t a0l, uint32_t a1, uint32_t a1l, uint32_t a2, uint32_t a2l,
+                                                 uint32_t b0, uint32_t b1, uint32_t b2) {
+  asm volatile(VQVS_MMA_HEAD_
+               VQVS_MMA_("%5", "%11", "p") VQVS_MMA_("%6", "%11", "t")
+               VQVS_MMA_("%7", "%12", "t") VQVS_MMA_("%8", "%12", "t")
+               VQVS_MMA_("%9", "%13", "t") VQVS_MMA_("%10", "%13", "t")
+               "}" ::"r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf),
+               "r"(a0), "r"(a0l), "r"(a1), "r"(a1l), "r"(a2), "r"(a2l), "r"(b0), "r"(b1), "r"(b2)
+               : "memory");
+}
+__device__ __forceinline__ void mma_group_stack1(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                 uint32_t a0, uint32_t a0l, uint32_t b0) {
+  asm volatile(VQVS_MMA_HEAD_ VQVS_MMA_("%5", "%7", "p") VQVS_MMA_("%6", "%7", "t") "}" ::"r"(d), "r"(ahi), "r"(bhi), "r"(idesc),
+               "r"(accf), "r"(a0), "r"(a0l), "r"(b0)
+               : "memory");
+}
+// separate W_hi / W_lo tiles: hi*hi + lo*hi + hi*lo per tap
+__device__ __forceinline__ void mma_group_split3(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                 uint32_t a0, uint32_t a0l, uint32_t a1, uint32_t a1l, uint32_t a2, uint32_t a2l,
+                                                 uint32_t b0, uint32_t b0l, uint32_t b1, uint32_t b1l, uint32_t b2, uint32_t b2l) {
+  asm volatile(VQVS_MMA_HEAD_
+               VQVS_MMA_("%5", "%11", "p") VQVS_MMA_("%6", "%11", "t") VQVS_MMA_("%5", "%12", "t")
+               VQVS_MMA_("%7", "%13", "t") VQVS_MMA_("%8", "%13", "t") VQVS_MMA_("%7", "%14", "t")
+               VQVS_MMA_("%9", "%15", "t") VQVS_MMA_("%10", "%15", "t") VQVS_MMA_("%9", "%16", "t")
+               "}" ::"r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf),
+               "r"(a0), "r"(a0l), "r"(a1), "r"(a1l), "r"(a2), "r"(a2l), "r"(b0), "r"(b0l), "r"(b1), "r"(b1l), "r"(b2), "r"(b2l)
+               : "memory");
+}
+__device__ __forceinline__ void mma_group_split1(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                 uint32_t a0, uint32_t a0l, uint32_t b0, uint32_t b0l) {
+  asm volatile(VQVS_MMA_HEAD_ VQVS_MMA_("%5", "%7", "p") VQVS_MMA_("%6", "%7", "t") VQVS_MMA_("%5", "%8", "t") "}" ::"r"(d),
+               "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf), "r"(a0), "r"(a0l), "r"(b0), "r"(b0l)
+               : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -726,18 +786,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   // KIND 3 = PLAIN and additionally no 1x1-skip stages and resident weights (conv1 and identity-skip conv2 of every
   // 64-channel layer: the largest share of a step)
   constexpr bool LEAN = KIND != 0, PLAIN = KIND >= 2, SIMPLE = KIND == 3;
+  constexpr bool STACKED = SIMPLE;  // the host selects KIND 3 only for stacked [W_hi ; W_lo] weight tiles of k = 3 convs
   extern __shared__ __align__(128) uint8_t smem[];
-  // mbarriers: raw_full[16] raw_empty[16] b_full[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
+  // mbarriers: raw_full[8] raw_empty[8] b_full[8] b_empty[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
 #define RAW_FULL(i) (bar0 + 8u * (i))
-#define RAW_EMPTY(i) (bar0 + 8u * (16 + (i)))
-#define B_FULL(i) (bar0 + 8u * (32 + (i)))
-#define A_FULL(i) (bar0 + 8u * (40 + (i)))
-#define AB_EMPTY(i) (bar0 + 8u * (48 + (i)))
-#define ACC_FULL(i) (bar0 + 8u * (56 + (i)))
-#define ACC_EMPTY(i) (bar0 + 8u * (58 + (i)))
-#define W_FULL (bar0 + 8u * 60)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 61 * 8);
+#define RAW_EMPTY(i) (bar0 + 8u * (8 + (i)))
+#define B_FULL(i) (bar0 + 8u * (16 + (i)))
+#define B_EMPTY(i) (bar0 + 8u * (24 + (i)))
+#define A_FULL(i) (bar0 + 8u * (32 + (i)))
+#define AB_EMPTY(i) (bar0 + 8u * (40 + (i)))
+#define ACC_FULL(i) (bar0 + 8u * (48 + (i)))
+#define ACC_EMPTY(i) (bar0 + 8u * (50 + (i)))
+#define W_FULL (bar0 + 8u * 52)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 53 * 8);
   float2* s_ss = reinterpret_cast<float2*>(smem + g.off_ss);    // (scale, shift) of the current sample
   float* s_bias = reinterpret_cast<float*>(smem + g.off_bias);
   const int c_in = d.c_a + d.c_b;
@@ -766,8 +828,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       mbar_init(RAW_FULL(i), 1);
       mbar_init(RAW_EMPTY(i), XFORM_WARPS);
     }
-    for (int i = 0; i < MAX_AB_SLOTS; ++i) {
+    for (int i = 0; i < MAX_B_SLOTS; ++i) {
       mbar_init(B_FULL(i), 1);
+      mbar_init(B_EMPTY(i), 1);
+    }
+    for (int i = 0; i < MAX_AB_SLOTS; ++i) {
       mbar_init(A_FULL(i), XFORM_WARPS);
       mbar_init(AB_EMPTY(i), 1);
     }
@@ -1028,25 +1093,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
       }
     } else {
-      Ring ab(g.ab_slots);
-      const uint32_t b_base = smem_u32(smem + g.off_ab + MT * g.kbs * g.a_kb_bytes);
+      Ring br(g.b_slots);
+      const uint32_t b_base = smem_u32(smem + g.off_b);
+      const int nkb_all = g.nkb_main + g.nkb_skip;
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         const int nt = it_nt;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)nt * g.per_tile_bytes;
-        for (int st = 0; st < total_stages; ++st) {
-          const bool is_skip = !SIMPLE && st >= g.main_stages;
-          const int kb0 = (is_skip ? st - g.main_stages : st) * g.kbs;
-          const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
-          const uint32_t bytes = nk * (is_skip ? g.b_unit_skip : g.b_unit_main);
-          mbar_wait(AB_EMPTY(ab.idx), ab.ph ^ 1);
+        for (int kb = 0; kb < nkb_all; ++kb) {  // one K block of weights per slot; the image is laid out in pipeline order
+          const uint32_t bytes = kb < g.nkb_main ? g.b_unit_main : g.b_unit_skip;
+          mbar_wait(B_EMPTY(br.idx), br.ph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(B_FULL(ab.idx), bytes);
-            tma_bulk_g2s(b_base + ab.idx * g.ab_slot_bytes, src, bytes, B_FULL(ab.idx));
+            mbar_expect_tx(B_FULL(br.idx), bytes);
+            tma_bulk_g2s(b_base + br.idx * g.b_slot_bytes, src, bytes, B_FULL(br.idx));
           }
           __syncwarp();
-          src += bytes;  // the image is laid out in pipeline order
-          ab.next();
+          src += bytes;
+          br.next();
         }
       }
     }
@@ -1055,13 +1118,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const uint32_t idesc = make_idesc((g.stack ? 2 : 1) * g.n_tile);
     // descriptor = constant fields + (address >> 4); the address field never carries into LBO
     const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, (g.stack ? 2 : 1) * g.n_tile * 16, 128);
+    const uint32_t a_lo_c = (uint32_t)a_const, a_hi32 = (uint32_t)(a_const >> 32);
+    const uint32_t b_lo_c = (uint32_t)b_const, b_hi32 = (uint32_t)(b_const >> 32);
     const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
     const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
     const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
     const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
     const uint32_t a_kb16 = g.a_kb_bytes >> 4;
-    if (SIMPLE || g.w_resident) mbar_wait(W_FULL, 0);
-    Ring ab(g.ab_slots);
+    const bool streamed = !SIMPLE && !g.w_resident;
+    const uint32_t b_base16 = smem_u32(smem + g.off_b) >> 4, b_slot16 = g.b_slot_bytes >> 4;
+    if (!streamed) mbar_wait(W_FULL, 0);
+    Ring ab(g.ab_slots), br(g.b_slots ? g.b_slots : 1);
     PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && lane == 0);
     for (int k_local = 0; k_local < n_my_tiles; ++k_local) {
       const int buf = k_local % g.nbuf;
@@ -1075,7 +1142,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       for (int st = 0; st < total_stages; ++st) {
         PROF_ADD(1, tprev);
         mbar_wait(A_FULL(ab.idx), ab.ph);
-        if (!SIMPLE && !g.w_resident) mbar_wait(B_FULL(ab.idx), ab.ph);
         tc_fence_after();
         PROF_ADD(0, tprev);
         const bool is_skip = !SIMPLE && st >= g.main_stages;
@@ -1083,44 +1149,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         const int nk = min(g.kbs, (is_skip ? g.nkb_skip : g.nkb_main) - kb0);
         const uint32_t a16 = ab_base16 + ab.idx * ab_slot16;
         const uint32_t unit16 = is_skip ? unit_skip16 : unit_main16;
-        const uint32_t b16 = (SIMPLE || g.w_resident) ? w16 : a16 + MT * g.kbs * a_kb16;
-        w16 += nk * unit16;
-        const int taps = is_skip ? 1 : d.ksize;
+        const int taps = SIMPLE ? 3 : is_skip ? 1 : d.ksize;
         const uint32_t tap_rows = is_skip ? 0u : (uint32_t)d.dilation;  // 16-B rows per tap shift
-        // Descriptors advance by warp-uniform adds computed by ALL lanes (uniform datapath); only the tcgen05 instructions
-        // themselves sit under the elected-lane predicate.  (With the arithmetic inside the elected branch the compiler
-        // built every descriptor in vector registers and moved it over with R2UR: ~100+ cycles of scalar work per MMA,
-        // twice the 67 cycles the tensor pipe needs -- tools/mma_bench.cu.)
+        // Descriptor low words advance by warp-uniform 32-bit adds computed by ALL lanes (uniform datapath); the MMAs of
+        // one K block and one time tile sit behind ONE elected branch (mma_group_*).
         const bool issue = elect_one();
-        const bool do_mma = !(dbg_flags & 4);
-        uint64_t da_j = a_const + a16;
-        const uint64_t db_0 = b_const + b16;
+        const bool do_mma = issue && !(dbg_flags & 4);
+        uint32_t a_k = a_lo_c + a16;
         const uint32_t a_step_j = g.kbs * a_kb16;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-          const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
-          uint32_t accj = acc;  // 0 only for the first MMA of each accumulator of the item
-          uint64_t da_k = da_j, db_k = db_0;
+        const uint32_t tap2 = 2 * tap_rows;
 #pragma unroll 1
-          for (int k = 0; k < nk; ++k) {
-            uint64_t da = da_k, db = db_k;
+        for (int k = 0; k < nk; ++k) {
+          uint32_t b_k;
+          if (streamed) {  // this K block's weights: one slot of the weight ring
+            mbar_wait(B_FULL(br.idx), br.ph);
+            tc_fence_after();
+            b_k = b_lo_c + b_base16 + br.idx * b_slot16;
+          } else {
+            b_k = b_lo_c + w16;
+            w16 += unit16;
+          }
+          const uint32_t accf = acc | (uint32_t)(k != 0);  // 0 only for the first MMA of each accumulator of the item
+          uint32_t a_j = a_k;
 #pragma unroll
-            for (int tap = 0; tap < 3; ++tap) {
-              if (tap < taps) {
-                if (issue && do_mma) {
-                  mma_bf16(d_tmem, da, db, idesc, accj);
-                  mma_bf16(d_tmem, da + a_lo_off, db, idesc, 1);
-                  if (!g.stack) mma_bf16(d_tmem, da, db + b_lo_off, idesc, 1);
-                }
-                accj = 1;
-                da += tap_rows;
-                db += b_tap_off;
+          for (int j = 0; j < MT; ++j) {  // the time tiles of the item share the K block's weights
+            const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
+            if (taps == 3) {
+              if (STACKED || g.stack) {
+                if (do_mma)
+                  mma_group_stack3(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, a_j + tap_rows, a_j + tap_rows + a_lo_off,
+                                   a_j + tap2, a_j + tap2 + a_lo_off, b_k, b_k + b_tap_off, b_k + 2 * b_tap_off);
+              } else {
+                if (do_mma)
+                  mma_group_split3(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, a_j + tap_rows, a_j + tap_rows + a_lo_off,
+                                   a_j + tap2, a_j + tap2 + a_lo_off, b_k, b_k + b_lo_off, b_k + b_tap_off, b_k + b_tap_off + b_lo_off,
+                                   b_k + 2 * b_tap_off, b_k + 2 * b_tap_off + b_lo_off);
+              }
+            } else {
+              if (STACKED || g.stack) {
+                if (do_mma) mma_group_stack1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, b_k);
+              } else {
+                if (do_mma) mma_group_split1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, b_k, b_k + b_lo_off);
               }
             }
-            da_k += a_kb16;
-            db_k += unit16;
+            a_j += a_step_j;
           }
-          da_j += a_step_j;
+          if (streamed) {
+            if (issue) mma_commit(B_EMPTY(br.idx));  // the weight slot is free once these MMAs have read it
+            __syncwarp();
+            br.next();
+          }
+          a_k += a_kb16;
         }
         if (issue) {
           mma_commit(AB_EMPTY(ab.idx));
@@ -1517,6 +1596,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 #undef RAW_FULL
 #undef RAW_EMPTY
 #undef B_FULL
+#undef B_EMPTY
 #undef A_FULL
 #undef AB_EMPTY
 #undef ACC_FULL
@@ -1872,7 +1952,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   // (PLAIN kinds compile the staging pitches in: 136 floats for the main taps at dilation 1 or 2, 128 for the 1x1 skip)
   const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE) &&
                      g.main_box_w == umma::SIMPLE_BOXW && (g.nkb_skip == 0 || g.skip_box_w == umma::TILE_M);
-  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1;
+  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1 && g.stack && d->ksize == 3;
   const int kind = !lean ? 0 : simple ? 3 : plain ? 2 : 1;
   cudaError_t le = kind == 3   ? umma::launch_kind3(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
                    : kind == 2 ? umma::launch_kind2(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
@@ -1884,6 +1964,17 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     return VQVS_ECUDA;
   }
   VQVS_CHECK_LAUNCH("vqvs_conv1d_umma");
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_debug_geo(const VqvsConv* d, int* out16) {
+  VQVS_CHECK_ARG(d && out16, "debug_geo: null pointer");
+  Geo g;
+  VQVS_CHECK_ARG((d->ksize == 1 || d->ksize == 3) && d->dilation >= 1 && d->dilation <= 32 && umma_geo(d, &g),
+                 "debug_geo: shape not supported by the tcgen05 path");
+  const int v[16] = {g.n_tiles, g.n_tile, g.stack, g.w_resident, g.kbs, g.mt, g.nbuf, g.ab_slots, g.ab_slot_bytes, g.raw_slots,
+                     g.raw_slot_bytes, g.smem_bytes, g.tma, g.main_stages, g.skip_stages, g.b_slots};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return VQVS_OK;
 }
 

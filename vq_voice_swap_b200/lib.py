@@ -109,6 +109,7 @@ SIGNATURES = {
     "vqvs_run": (C.c_int, [C.POINTER(Op), C.c_int, _p]),
     "vqvs_run_timed": (C.c_int, [C.POINTER(Op), C.c_int, _p, C.POINTER(C.c_float)]),
     "vqvs_debug_prof": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "vqvs_debug_geo": (C.c_int, [C.POINTER(Conv), C.POINTER(C.c_int)]),
     "vqvs_umma_selftest": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
 }
 
