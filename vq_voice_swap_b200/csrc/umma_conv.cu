@@ -487,13 +487,10 @@ __device__ __forceinline__ void gelu4p(uint64_t* y) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) q[i] = mul2(q[i], t[i]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = mul2(q[i], e[i]);  // 0.5*erfc(|y|/sqrt2)
+  for (int i = 0; i < 4; ++i) q[i] = fma2(q[i], e[i], bcast2(-0.5f));  // 0.5*erfc(|y|/sqrt2) - 0.5
+  // gelu(y) = relu(y) - |y|*0.5*erfc(|y|/sqrt2) = 0.5*y + (-|y|)*(0.5*erfc(|y|/sqrt2) - 0.5): packed throughout (no scalar max)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a, b;
-    unpack2(y[i], a, b);
-    y[i] = fma2(nay[i], q[i], pack2(fmaxf(a, 0.f), fmaxf(b, 0.f)));
-  }
+  for (int i = 0; i < 4; ++i) y[i] = fma2(nay[i], q[i], mul2(y[i], bcast2(0.5f)));
 }
 
 // 4 packed pairs (8 consecutive channels of one position) -> bf16 hi / lo operand rows (16 B each)
@@ -958,7 +955,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           // the whole stage; the 9th warp transforms the halo rows of every chunk.
           const int chunks = 2 * nk;                       // 2, 4 or 8 (stage sizes are 1, 2 or 4 K blocks)
           const int q = mwarp & (chunks - 1);
-          const int row_first = (mwarp / chunks) * (16 * chunks) + lane;  // 8/chunks warps share a chunk
+          const int csh = nk == 1 ? 1 : nk == 2 ? 2 : 3;                    // log2(chunks)
+          const int row_first = ((mwarp >> csh) << (4 + csh)) + lane;      // 8/chunks warps share a chunk, 16*chunks rows each
           for (int j = 0; j < MT; ++j, v.x0 += step, v.tcs += TILE_M) {  // the time tiles of this item share the stage's weights
             const uint8_t* raw = smem + g.off_raw + rw.idx * g.raw_slot_bytes + j * g.kbs * g.raw_kb_bytes;
             uint8_t* a_slot = a_slot0 + j * g.kbs * g.a_kb_bytes;
@@ -1316,34 +1314,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const uint32_t acc_addr = tmem_base + (buf * MT + j) * g.acc_cols + ((uint32_t)(quarter * 32) << 16);
           const int t = t0 + j * TILE_M + row;
           const bool t_ok = t < d.t_out;
-          // identity-skip operands of one 8-column piece (raw block input, resized on the fly)
-          auto load_skip = [&](int c0_, float* dst) {
+          // Output and identity-skip pointers WALK the tile (8 channels per piece, one 64-bit multiply-add per access): a full
+          // index computation per piece cost ~12 integer instructions of the ~66 a piece takes (ncu, profiles/r2_*).
+          float* op = d.out + ((size_t)n * d.c_out + nt * g.n_tile + half * 32) * d.t_out + t;
+          const int ts_out = d.t_out, ts_skip = d.t_skip;
+          const float* skp = nullptr;
+          auto skip_chunk = [&](int c0_) {  // first piece of a 32-channel chunk (chunks never straddle the two concat sources)
             const int co_ = nt * g.n_tile + c0_;
             const float* sp = co_ < d.s_a ? d.sa + ((size_t)n * d.s_a + co_) * d.t_skip
                                           : d.sb + ((size_t)n * d.s_b + (co_ - d.s_a)) * d.t_skip;
+            skp = sp + (SKIPK == 1 ? (t >> skip_shift) : 2 * t);
+          };
+          // identity-skip operands of the next 8-column piece (raw block input, resized on the fly)
+          auto load_skip = [&](float* dst) {
+            const float* p = skp;
             if (SKIPK == 1) {
-              sp += t >> skip_shift;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = __ldg(sp + (size_t)i * d.t_skip);
-            } else {
-              sp += 2 * t;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 p = __ldg(reinterpret_cast<const float2*>(sp + (size_t)i * d.t_skip));
-                dst[i] = 0.5f * (p.x + p.y);
+                dst[i] = __ldg(p);
+                p += ts_skip;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 pr = __ldg(reinterpret_cast<const float2*>(p));
+                dst[i] = 0.5f * (pr.x + pr.y);
+                p += ts_skip;
               }
             }
+            skp = p;
           };
           float sk[8], skn[8];
           // the first piece's operands are requested BEFORE waiting for the accumulator, each later piece's while
           // the previous piece is being stored (the next item's lines were already prefetched into L2 above)
-          if (SKIPK != 0 && t_ok) load_skip(half * 32, sk);
+          if (SKIPK != 0 && t_ok) {
+            skip_chunk(half * 32);
+            load_skip(sk);
+          }
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
 #pragma unroll
             for (int sub = 0; sub < 4; ++sub) {
               const int c0 = (half + EPI_SPLIT * c) * 32 + sub * 8;  // first column of this 8-wide piece
-              const int co0 = nt * g.n_tile + c0;
               if (!waited) {
                 PROF_ADD(1, tprev);
                 mbar_wait(ACC_FULL(buf), acc_par);
@@ -1357,8 +1369,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               constexpr int kLast = 4 * NCH - 1;
               const bool has_next = c * 4 + sub < kLast;
               if (SKIPK != 0 && t_ok && has_next) {
-                const int nsub = (sub + 1) & 3, nc = c + (sub == 3 ? 1 : 0);
-                load_skip((half + EPI_SPLIT * nc) * 32 + nsub * 8, skn);
+                if (sub == 3) skip_chunk((half + EPI_SPLIT * (c + 1)) * 32);
+                load_skip(skn);
               }
               tmem_ld_wait();
               if (j == MT - 1 && c == NCH - 1 && sub == 3) {  // last TMEM read of the item: hand the accumulators back
@@ -1368,7 +1380,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               if (t_ok && !(dbg_flags & 16)) {
                 const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
                 const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float* outp = d.out + ((size_t)n * d.c_out + co0) * d.t_out + t;
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {  // packed fp32x2 adds: accumulator (+ lo half) + bias (+ skip)
@@ -1377,8 +1388,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   if (SKIPK != 0) o = add2(o, pack2(sk[2 * i], sk[2 * i + 1]));
                   unpack2(o, v[2 * i], v[2 * i + 1]);
                 }
+                {
+                  float* p = op;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) outp[(size_t)i * d.t_out] = v[i];
+                  for (int i = 0; i < 8; ++i) {
+                    *p = v[i];
+                    p += ts_out;
+                  }
+                }
                 if (stats && !(dbg_flags & 128)) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -1387,6 +1404,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   }
                 }
               }
+              op += (sub == 3 ? 8 + 32 * (EPI_SPLIT - 1) : 8) * (ptrdiff_t)ts_out;  // next piece (next chunk of this warp after 4)
               if (SKIPK != 0 && has_next) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sk[i] = skn[i];
@@ -1946,7 +1964,8 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     g.epi_nch = nch;
     g.epi_na = na;
     g.epi_fast = gran_ok && !(g.n_tile & 31) && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * umma::EPI_SPLIT &&
-                 !(d->reserved_ & 32);
+                 !(d->reserved_ & 32) &&
+                 !(d->skip_mode == VQVS_SKIP_IDENTITY && d->s_b && (d->s_a & 31));  // skip chunks of 32 channels stay in one source
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
   // (PLAIN kinds compile the staging pitches in: 136 floats for the main taps at dilation 1 or 2, 128 for the 1x1 skip)
