@@ -278,6 +278,11 @@ int vqvs_run(const VqvsOp* ops, int n_ops, void* stream);
  * in milliseconds (synchronises the stream at the end; measurement aid for bench.py). */
 int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 
+/* Ops executed by vqvs_run / vqvs_run_timed since the library was loaded, indexed by VQVS_OP_* (out16[VQVS_OP_CONV_UMMA] =
+ * tcgen05 conv launches, ...; memsets are counted under VQVS_OP_MEMSET).  Evidence hook for the script-level tests and
+ * bench.py's gpu_launches: a run that went through a fallback would leave these at zero. */
+int vqvs_launch_counts(unsigned long long* out16);
+
 /* Role profiler of the last vqvs_conv1d_umma launched with debug flag 512 (cycles per phase of CTA 0):
  * [0..3] transform warp 0: wait operand slot, wait raw, work, loop; [4..7] TMA; [8..11] MMA; [12..15] epilogue. */
 int vqvs_debug_prof(unsigned long long* host32);

@@ -17,6 +17,9 @@ void set_error(const char* fmt, ...) {
 
 int run_film(const VqvsFilm* f, void* stream);
 
+// kernels launched through vqvs_run / vqvs_run_timed since the library was loaded, per op kind (vqvs_launch_counts)
+static unsigned long long g_launches[16];
+
 }  // namespace vqvs
 
 extern "C" int vqvs_abi_version(void) { return VQVS_ABI_VERSION; }
@@ -101,7 +104,17 @@ static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev)
       vqvs::set_error("vqvs_run: op %d (kind %d) failed: %s", i, ops[i].kind, msg);
       return rc;
     }
+    if (ops[i].kind > 0 && ops[i].kind < 16) __atomic_fetch_add(&vqvs::g_launches[ops[i].kind], 1ull, __ATOMIC_RELAXED);
     if (ev) cudaEventRecord(ev[i + 1], (cudaStream_t)stream);
   }
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_launch_counts(unsigned long long* out16) {
+  if (!out16) {
+    vqvs::set_error("vqvs_launch_counts: null pointer");
+    return VQVS_EINVAL;
+  }
+  for (int i = 0; i < 16; ++i) out16[i] = __atomic_load_n(&vqvs::g_launches[i], __ATOMIC_RELAXED);
   return VQVS_OK;
 }

@@ -108,6 +108,7 @@ SIGNATURES = {
     "vqvs_vq_embed": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_run": (C.c_int, [C.POINTER(Op), C.c_int, _p]),
     "vqvs_run_timed": (C.c_int, [C.POINTER(Op), C.c_int, _p, C.POINTER(C.c_float)]),
+    "vqvs_launch_counts": (C.c_int, [C.POINTER(C.c_uint64)]),
     "vqvs_debug_prof": (C.c_int, [C.POINTER(C.c_uint64)]),
     "vqvs_debug_geo": (C.c_int, [C.POINTER(Conv), C.POINTER(C.c_int)]),
     "vqvs_umma_selftest": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
@@ -142,6 +143,18 @@ def check(rc: int, what: str = "libvqvs") -> None:
     if rc != 0:
         msg = load().vqvs_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+OP_NAMES = {OP_CONV_SIMT: "conv_simt", OP_CONV_UMMA: "conv_umma", OP_GN_FINALIZE: "gn_finalize", OP_CONV_IN: "conv_in",
+            OP_CONV_OUT: "conv_out", OP_TIME_EMBED: "time_embed", OP_FILM: "film", OP_MEMSET: "memset",
+            OP_DDPM_FINISH: "ddpm_finish"}
+
+
+def launch_counts() -> dict:
+    """Ops executed through vqvs_run since the library was loaded, by name (include/vqvs.h: vqvs_launch_counts)."""
+    buf = (C.c_uint64 * 16)()
+    check(load().vqvs_launch_counts(buf), "vqvs_launch_counts")
+    return {name: int(buf[kind]) for kind, name in OP_NAMES.items()}
 
 
 def stream_ptr() -> int:
