@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 2
+#define VQVS_ABI_VERSION 3
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -74,6 +74,16 @@ int vqvs_device_info(int* cc, int* sm_count);
  * consecutive, G-aligned channels into the first channel's slot (requires VQVS_CONV_PAIR_STATS; 0 means G = 2).
  * Valid when every consuming GroupNorm group is a union of whole G-granules of this tensor. */
 #define VQVS_CONV_STAT_GRAN_SHIFT 12
+/* bits 16..17 of VqvsConv.reserved_: tensor-core operand format of vqvs_conv1d_umma; must match the format the weight
+ * image was packed with (vqvs_pack_conv_weights).
+ *   VQVS_PREC_BF16X3  activations and weights split into bf16 hi + lo, three products per tap (~2^-16 relative operand
+ *                     error; unet64 forward 1.2e-5 vs the fp32 oracle) -- the default;
+ *   VQVS_PREC_F16     one fp16 x fp16 product per tap (2^-11 operand rounding).  Meant for the deep, tensor-bound
+ *                     levels only: with every conv of C_out >= 4*base_channels in this format a UNet forward stays at
+ *                     6e-5 (tools/precision_study.py), a third of the tensor work of those layers. */
+#define VQVS_CONV_PREC_SHIFT 16
+#define VQVS_PREC_BF16X3 0
+#define VQVS_PREC_F16 1
 
 struct VqvsGnFinalize; /* defined below */
 
@@ -117,11 +127,12 @@ int vqvs_conv1d_fused(const VqvsConv* d, void* stream);
 int vqvs_conv1d_umma(const VqvsConv* d, void* stream);
 /* 1 if vqvs_conv1d_umma accepts this descriptor. */
 int vqvs_conv1d_umma_supported(const VqvsConv* d);
-/* Bytes of the packed operand image for a conv (main taps + optional 1x1 skip). */
-int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip);
+/* Bytes of the packed operand image for a conv (main taps + optional 1x1 skip) in operand format `prec`
+ * (VQVS_PREC_BF16X3 / VQVS_PREC_F16); -1 if the shape is not supported. */
+int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip, int prec);
 /* Build the image from fp32 weights w[c_out,c_in,ksize], w_skip[c_out,c_skip] (device). */
 int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c_out, int c_in, int ksize,
-                           int c_skip, void* packed, void* stream);
+                           int c_skip, int prec, void* packed, void* stream);
 
 /*
  * GroupNorm statistics -> per-(sample, channel) affine, with optional FiLM:

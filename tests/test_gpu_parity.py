@@ -343,9 +343,16 @@ WIDE_CASES = {
 }
 
 
+# operand format -> tolerance of one ResBlock: bf16 hi/lo split (three products) vs ONE fp16 product per tap (the format of
+# the deep levels, engine.conv_precision; 2^-11 operand rounding)
+PREC_TOL = {"bf16x3": 1e-4, "f16": 1e-3}
+
+
+@pytest.mark.parametrize("prec", sorted(PREC_TOL))
 @pytest.mark.parametrize("name", sorted(WIDE_CASES))
-def test_resblock_wide_vs_oracle(name, monkeypatch):
+def test_resblock_wide_vs_oracle(name, prec, monkeypatch):
     monkeypatch.setenv("VQVS_BACKEND", "umma")
+    monkeypatch.setenv("VQVS_PREC", prec)
     from vq_voice_swap_b200.unet import ResBlock
 
     c, co, t, sf, dil, batch = WIDE_CASES[name]
@@ -356,7 +363,7 @@ def test_resblock_wide_vs_oracle(name, monkeypatch):
     emb = synth.normal(f"wide/{name}/emb", (batch, 256))
     ref = O.resblock(x, emb, sd, "", scale_factor=sf, dilation=dil)
     got = blk.to(DEV)(x.to(DEV), emb.to(DEV)).cpu()
-    assert rel_l2(got, ref) <= 1e-4
+    assert rel_l2(got, ref) <= PREC_TOL[prec]
     # a second call on the same plan (statistics arena re-zeroed, weights resident) must give the same answer
     again = blk(x.to(DEV), emb.to(DEV)).cpu()
     assert rel_l2(again, got) <= 1e-6
@@ -381,7 +388,24 @@ def test_full_size_forward_vs_oracle(unet64, monkeypatch):
     torch.set_num_threads(max(1, torch.get_num_threads()))
     ref = O.unet_predictor(sd, x, ts)
     got = m.predictor(x.to(DEV), ts.to(DEV)).cpu()
-    assert rel_l2(got, ref) <= 1e-3  # north_star tolerance; measured ~2e-5
+    # north_star allows 1e-3; the per-level operand formats (bf16x3, fp16 for C_out >= 256) are chosen to stay under 2e-4
+    assert rel_l2(got, ref) <= 2e-4
+
+
+def test_full_size_trajectory_vs_oracle(unet64, monkeypatch):
+    """A 4-step unet64 DDPM trajectory at T = 64000 with injected noise against the CPU oracle (errors of successive
+    forwards compound through the sampler; tools/measure_parity.py reports the 50-step figure)."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    m, sd = unet64
+    steps = 4
+    x_T = synth.normal("drift/x_T", (1, 1, 64000))
+    noises = [synth.normal(f"drift/n{i}", x_T.shape) for i in range(steps)]
+    it = iter(noises)
+    monkeypatch.setattr(torch, "randn_like", lambda t, **k: next(it).to(t))
+    got = m.diffusion.ddpm_sample(x_T.to(DEV), m.predictor, steps).cpu()
+    monkeypatch.undo()
+    ref = O.ddpm_sample(O.make_alpha_bar("exp"), x_T, lambda a, b: O.unet_predictor(sd, a, b), steps, noises)
+    assert rel_l2(got, ref) <= 1e-3
 
 
 def test_batch_64_samples_are_independent(unet64, monkeypatch):
@@ -394,5 +418,7 @@ def test_batch_64_samples_are_independent(unet64, monkeypatch):
     full = m.predictor(x, ts)
     for i in (0, 37, 63):
         alone = m.predictor(x[i:i + 1].contiguous(), ts[i:i + 1].contiguous())
-        assert rel_l2(alone.cpu(), full[i:i + 1].cpu()) <= 1e-5
+        # (1e-5 with bf16x3 everywhere; the fp16 operands of the deep levels round 1e-7 differences in the GroupNorm statistics
+        # -- atomic summation order -- to whole fp16 ulps in a few elements)
+        assert rel_l2(alone.cpu(), full[i:i + 1].cpu()) <= 1e-4
     assert torch.isfinite(full).all()

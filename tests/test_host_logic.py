@@ -70,8 +70,10 @@ def test_bad_arguments_return_errors_not_crashes(built):
     assert lib.vqvs_conv1d_fused(C.byref(d), None) == -1
     assert b"conv" in lib.vqvs_last_error()
     assert lib.vqvs_run(None, 3, None) == -1
-    assert lib.vqvs_packed_weight_bytes(64, 24, 3, 0) == -1  # 24 channels: not a multiple of 16
-    assert lib.vqvs_packed_weight_bytes(64, 128, 3, 128) == (128 * 3 + 128) * 64 * 4
+    assert lib.vqvs_packed_weight_bytes(64, 24, 3, 0, 0) == -1  # 24 channels: not a multiple of 16
+    assert lib.vqvs_packed_weight_bytes(64, 128, 3, 128, 0) == (128 * 3 + 128) * 64 * 4   # bf16 hi + lo
+    assert lib.vqvs_packed_weight_bytes(64, 128, 3, 128, 1) == (128 * 3 + 128) * 64 * 2   # one fp16 image
+    assert lib.vqvs_packed_weight_bytes(64, 128, 3, 128, 7) == -1                         # unknown operand format
 
 
 STATE_TABLES = {

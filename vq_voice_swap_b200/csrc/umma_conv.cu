@@ -24,6 +24,7 @@
 // translation units; measurements behind the design choices: tools/mma_bench.cu, tools/alu_bench.cu, profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -61,6 +62,7 @@ struct Geo {
   int pad, rows;            // halo and operand rows (= 128 + 2*pad)
   int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
   int epi_fast, epi_nch, epi_na;  // register-statistics epilogue: eligible / 32-column chunks per warp / accumulators per chunk
+  int prec;                 // operand format: VQVS_PREC_BF16X3 (hi/lo split, three products) or VQVS_PREC_F16 (one fp16 product)
   int stack;                // 1: weight rows are [W_hi ; W_lo] (N = 2*n_tile): two MMAs per tap give all four
                             //    hi/lo products, the epilogue adds the two column halves
   int a_kb_bytes;           // operand bytes per K block: hi+lo, 2 chunks, `rows` rows of 16 B
@@ -91,7 +93,7 @@ __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g,
-                     int prefer_mt = 0) {
+                     int prefer_mt = 0, int prec = 0) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
   g->n_tiles = (c_out + 255) / 256;
   if (c_out % g->n_tiles) return false;
@@ -101,14 +103,16 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->nkb_skip = c_skip / KBLK;
   g->pad = (ksize / 2) * dilation;
   g->rows = TILE_M + 2 * g->pad;
-  g->a_kb_bytes = g->rows * 64;
-  g->b_unit_main = ksize * g->n_tile * 64;
-  g->b_unit_skip = g->n_tile * 64;
+  g->prec = prec;
+  const int parts = prec == VQVS_PREC_F16 ? 1 : 2;  // operand images per K block: bf16 hi + lo, or one fp16
+  g->a_kb_bytes = g->rows * 32 * parts;
+  g->b_unit_main = ksize * g->n_tile * 32 * parts;
+  g->b_unit_skip = g->n_tile * 32 * parts;
   g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
   // Narrow layers: an MMA costs the same ~77 cycles for N = 64 and N = 128 (tools/mma_bench.cu), so stacking
   // W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs,
   // which also adds the lo*lo term).
-  g->stack = (g->n_tile == 32 || g->n_tile == 64) ? 1 : 0;
+  g->stack = (parts == 2 && (g->n_tile == 32 || g->n_tile == 64)) ? 1 : 0;
   int cols = 32;
   while (cols < (g->stack ? 2 : 1) * g->n_tile) cols *= 2;
   g->acc_cols = cols;
@@ -266,8 +270,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
          (1ull << 46);
 }
 // kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, bool f16 = false) {  // a/b format: 1 = bf16, 0 = fp16
+  const uint32_t fmt = f16 ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | fmt | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -316,6 +321,18 @@ __device__ __forceinline__ void mma_group_split3(uint32_t d, uint32_t ahi, uint3
                VQVS_MMA_("%9", "%15", "t") VQVS_MMA_("%10", "%15", "t") VQVS_MMA_("%9", "%16", "t")
                "}" ::"r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf),
                "r"(a0), "r"(a0l), "r"(a1), "r"(a1l), "r"(a2), "r"(a2l), "r"(b0), "r"(b0l), "r"(b1), "r"(b1l), "r"(b2), "r"(b2l)
+               : "memory");
+}
+// VQVS_PREC_F16: one product per tap
+__device__ __forceinline__ void mma_group_single3(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                  uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t b2) {
+  asm volatile(VQVS_MMA_HEAD_ VQVS_MMA_("%5", "%8", "p") VQVS_MMA_("%6", "%9", "t") VQVS_MMA_("%7", "%10", "t") "}" ::"r"(d),
+               "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf), "r"(a0), "r"(a1), "r"(a2), "r"(b0), "r"(b1), "r"(b2)
+               : "memory");
+}
+__device__ __forceinline__ void mma_group_single1(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
+                                                  uint32_t a0, uint32_t b0) {
+  asm volatile(VQVS_MMA_HEAD_ VQVS_MMA_("%5", "%6", "p") "}" ::"r"(d), "r"(ahi), "r"(bhi), "r"(idesc), "r"(accf), "r"(a0), "r"(b0)
                : "memory");
 }
 __device__ __forceinline__ void mma_group_split1(uint32_t d, uint32_t ahi, uint32_t bhi, uint32_t idesc, uint32_t accf,
@@ -408,7 +425,22 @@ __device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
   *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__device__ __forceinline__ void store_rows(const float* v, uint8_t* a_hi, uint8_t* a_lo, int row) {
+// 8 floats -> one 16-B row of fp16 (VQVS_PREC_F16 operands)
+__device__ __forceinline__ uint4 pack8h(const float* v) {
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hb = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+  }
+  return make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+__device__ __forceinline__ void store_rows(const float* v, uint8_t* a_hi, uint8_t* a_lo, int row, bool f16) {
+  if (f16) {
+    *reinterpret_cast<uint4*>(a_hi + row * 16) = pack8h(v);
+    return;
+  }
   uint4 hi, lo;
   split8(v, &hi, &lo);
   *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
@@ -524,7 +556,7 @@ struct Src {
 
 // Direct mode (no TMA: lengths not a multiple of 4): 8 channels [c8, c8+8) at conv-input position tc.
 __device__ __forceinline__ void produce_direct(const Src& s, int n, int c8, int tc, bool act, const float4* ss,
-                                               uint8_t* a_hi, uint8_t* a_lo, int row) {
+                                               uint8_t* a_hi, uint8_t* a_lo, int row, bool f16) {
   float v[8];
   if (tc < 0 || tc >= s.t_conv) {
 #pragma unroll
@@ -552,7 +584,7 @@ __device__ __forceinline__ void produce_direct(const Src& s, int n, int c8, int 
       if (act) affine_gelu8(v, ss);
     }
   }
-  store_rows(v, a_hi, a_lo, row);
+  store_rows(v, a_hi, a_lo, row, f16);
 }
 
 // Transposing butterfly: every lane holds v[0..31] (one row, 32 columns); afterwards lane l holds
@@ -590,7 +622,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 struct StageView {
   int rows;           // operand rows of this conv (row pitch of the hi/lo blocks)
   int box_w, boxes, x0, tcs, n_rows, t_src, t_conv, resize;
-  bool act;
+  bool act, f16;
 };
 
 // Row-wise work of one thread in one stage: rows row_first, row_first + 32, ... (NIT of them) of ONE 8-channel
@@ -663,12 +695,25 @@ __device__ __forceinline__ void transform_row_group(const StageView& v, const fl
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int row = row0 + 32 * r, tc = v.tcs + row;
-    uint4 hi, lo;
-    split4p(y[r], &hi, &lo);
     // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
-    if (tc < 0 || tc >= v.t_conv) hi = lo = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
-    *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+    const bool oob = tc < 0 || tc >= v.t_conv;
+    if (v.f16) {  // one fp16 operand row
+      uint32_t h[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a, b;
+        unpack2(y[r][i], a, b);
+        const __half2 hb = __floats2half2_rn(a, b);
+        h[i] = oob ? 0u : *reinterpret_cast<const uint32_t*>(&hb);
+      }
+      *reinterpret_cast<uint4*>(a_hi + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    } else {
+      uint4 hi, lo;
+      split4p(y[r], &hi, &lo);
+      if (oob) hi = lo = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
+      *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+    }
   }
 }
 
@@ -719,19 +764,11 @@ __device__ __forceinline__ void transform_up2(const StageView& v, const uint8_t*
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = 0.f;
   }
-  uint4 hi, lo;
-  split8(x, &hi, &lo);
   uint8_t* a_hi = a_k + chunk * (v.rows * 16);
   uint8_t* a_lo = a_hi + v.rows * 32;
   const int r0 = 2 * ts - v.tcs;
-  if (r0 >= 0 && r0 < v.n_rows) {
-    *reinterpret_cast<uint4*>(a_hi + r0 * 16) = hi;
-    *reinterpret_cast<uint4*>(a_lo + r0 * 16) = lo;
-  }
-  if (r0 + 1 >= 0 && r0 + 1 < v.n_rows) {
-    *reinterpret_cast<uint4*>(a_hi + (r0 + 1) * 16) = hi;
-    *reinterpret_cast<uint4*>(a_lo + (r0 + 1) * 16) = lo;
-  }
+  if (r0 >= 0 && r0 < v.n_rows) store_rows(x, a_hi, a_lo, r0, v.f16);
+  if (r0 + 1 >= 0 && r0 + 1 < v.n_rows) store_rows(x, a_hi, a_lo, r0 + 1, v.f16);
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -881,6 +918,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     vm.resize = d.resize;     vs.resize = d.skip_resize;
     vm.act = d.act && !(dbg_flags & 8);
     vs.act = false;
+    vm.f16 = vs.f16 = g.prec == VQVS_PREC_F16;
     const int main_step = (TILE_M * g.main_origin_mul) / 2, skip_step = (TILE_M * g.skip_origin_mul) / 2;
     TILE_ITER_INIT();
     for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
@@ -1003,7 +1041,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
             const int q = i / n_rows, row = i - q * n_rows;
             const int c8 = kb0 * KBLK + q * 8;
             uint8_t* a_hi = a_slot + (q >> 1) * g.a_kb_bytes + (q & 1) * (g.rows * 16);
-            produce_direct(src, n, c8, t0j - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row);
+            produce_direct(src, n, c8, t0j - pad + row, act, reinterpret_cast<const float4*>(s_ss + c8), a_hi, a_hi + g.rows * 32, row,
+                           g.prec == VQVS_PREC_F16);
           }
          }
         }
@@ -1113,12 +1152,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (warp-uniform loop, elected issue) ===========================
-    const uint32_t idesc = make_idesc((g.stack ? 2 : 1) * g.n_tile);
+    const bool f16 = !SIMPLE && g.prec == VQVS_PREC_F16;
+    const uint32_t idesc = make_idesc((g.stack ? 2 : 1) * g.n_tile, f16);
     // descriptor = constant fields + (address >> 4); the address field never carries into LBO
     const uint64_t a_const = make_desc(0, g.rows * 16, 128), b_const = make_desc(0, (g.stack ? 2 : 1) * g.n_tile * 16, 128);
     const uint32_t a_lo_c = (uint32_t)a_const, a_hi32 = (uint32_t)(a_const >> 32);
     const uint32_t b_lo_c = (uint32_t)b_const, b_hi32 = (uint32_t)(b_const >> 32);
-    const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * 64) >> 4;
+    const uint32_t a_lo_off = (g.rows * 32) >> 4, b_lo_off = (g.n_tile * 32) >> 4, b_tap_off = (g.n_tile * (f16 ? 32 : 64)) >> 4;
     const uint32_t ab_base16 = smem_u32(smem + g.off_ab) >> 4, ab_slot16 = g.ab_slot_bytes >> 4;
     const uint32_t w_base16 = smem_u32(smem + g.off_w) >> 4;
     const uint32_t unit_main16 = g.b_unit_main >> 4, unit_skip16 = g.b_unit_skip >> 4;
@@ -1172,7 +1212,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
 #pragma unroll
           for (int j = 0; j < MT; ++j) {  // the time tiles of the item share the K block's weights
             const uint32_t d_tmem = d_tmem0 + j * g.acc_cols;
-            if (taps == 3) {
+            if (f16) {
+              if (taps == 3) {
+                if (do_mma)
+                  mma_group_single3(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + tap_rows, a_j + tap2, b_k, b_k + b_tap_off,
+                                    b_k + 2 * b_tap_off);
+              } else {
+                if (do_mma) mma_group_single1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, b_k);
+              }
+            } else if (taps == 3) {
               if (STACKED || g.stack) {
                 if (do_mma)
                   mma_group_stack3(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, a_j + tap_rows, a_j + tap_rows + a_lo_off,
@@ -1266,7 +1314,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       };
       const int row = quarter * 32 + lane;
       const int skip_shift = d.skip_resize == VQVS_RESIZE_UP2 ? 1 : 0;
-      constexpr bool stack = NCH == 1;  // a 64-channel N tile is always stacked (make_geo), wider ones never
+      const bool stack = NCH == 1 && g.stack;  // only 32/64-channel N tiles of the bf16x3 format are stacked (make_geo)
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         TILE_COORDS(tile)
@@ -1692,8 +1740,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     const int nt = co / g.n_tile, row = co - nt * g.n_tile;
     const int kb = ci / KBLK, chunk = (ci % KBLK) / 8, e = ci % 8;
     long long off = (long long)nt * g.per_tile_bytes;
-    if (!skip) off += (long long)kb * g.b_unit_main + (long long)tap * (g.n_tile * 64);
+    const bool f16 = g.prec == VQVS_PREC_F16;
+    if (!skip) off += (long long)kb * g.b_unit_main + (long long)tap * (g.n_tile * (f16 ? 32 : 64));
     else off += (long long)g.nkb_main * g.b_unit_main + (long long)kb * g.b_unit_skip;
+    if (f16) {  // one fp16 image: [chunk][row][16 B]
+      off += (long long)chunk * (g.n_tile * 16) + (long long)row * 16 + e * 2;
+      *reinterpret_cast<__half*>(img + off) = __float2half_rn(val);
+      continue;
+    }
     // un-stacked: [hi: chunk][row][16 B] then [lo: ...]; stacked: [chunk][rows: hi 0..n_tile-1, lo n_tile..][16 B]
     off += (long long)chunk * ((g.stack ? 2 : 1) * g.n_tile * 16) + (long long)row * 16 + e * 2;
     const __nv_bfloat16 hi = __float2bfloat16_rn(val);
@@ -1806,10 +1860,12 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
   if (c_skip && (d->s_a % umma::KBLK || d->s_b % umma::KBLK)) return 0;
   if (d->resize == VQVS_RESIZE_DOWN2 && (d->t_in & 1)) return 0;  // paired loads need even rows
   const bool tma = tma_eligible(d);
+  const int prec = (d->reserved_ >> VQVS_CONV_PREC_SHIFT) & 3;
+  if (prec != VQVS_PREC_BF16X3 && prec != VQVS_PREC_F16) return 0;
   auto geo = [&](int prefer_mt) {
-    if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g, prefer_mt))
+    if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g, prefer_mt, prec))
       return true;
-    return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g, prefer_mt);
+    return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g, prefer_mt, prec);
   };
   if (!geo(0)) return 0;
   if (g->mt == 2 && d->batch > 0 && d->t_out > 0) {
@@ -1838,17 +1894,19 @@ extern "C" int vqvs_conv1d_umma_supported(const VqvsConv* d) {
   return d && (d->ksize == 1 || d->ksize == 3) && d->dilation >= 1 && d->dilation <= 32 && umma_geo(d, &g);
 }
 
-extern "C" int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip) {
+extern "C" int64_t vqvs_packed_weight_bytes(int c_out, int c_in, int ksize, int c_skip, int prec) {
   Geo g;
-  if (!umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g)) return -1;
+  if ((prec != VQVS_PREC_BF16X3 && prec != VQVS_PREC_F16) || !umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g, 0, prec))
+    return -1;
   return (int64_t)g.n_tiles * g.per_tile_bytes;
 }
 
-extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c_out, int c_in, int ksize, int c_skip,
+extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c_out, int c_in, int ksize, int c_skip, int prec,
                                       void* packed, void* stream) {
   Geo g;
   VQVS_CHECK_ARG(w && packed && (c_skip == 0 || w_skip), "pack_conv_weights: null pointer");
-  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g),
+  VQVS_CHECK_ARG(prec == VQVS_PREC_BF16X3 || prec == VQVS_PREC_F16, "pack_conv_weights: unknown operand format %d", prec);
+  VQVS_CHECK_ARG(umma::make_geo(c_in, c_out, ksize, 1, c_skip, 0, 0, false, &g, 0, prec),
                  "pack_conv_weights: unsupported shape c_out=%d c_in=%d k=%d skip=%d", c_out, c_in, ksize, c_skip);
   umma::pack_weights_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(w, w_skip, c_out, c_in, ksize, c_skip, g, (uint8_t*)packed);
   VQVS_CHECK_LAUNCH("vqvs_pack_conv_weights");

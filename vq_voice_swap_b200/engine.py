@@ -177,20 +177,42 @@ class Weights:
         self.signature = None
 
 
-def _pack(conv: torch.nn.Conv1d, skip: Optional[torch.nn.Conv1d]) -> Optional[torch.Tensor]:
+class Packed:
+    """tcgen05 operand image of one conv (+ its 1x1 skip) and the operand format it was built for."""
+
+    def __init__(self, img: torch.Tensor, prec: int):
+        self.img, self.prec = img, prec
+
+
+def conv_precision(c_out: int, base_channels: Optional[int]) -> int:
+    """Operand format of a predictor conv (include/vqvs.h VQVS_PREC_*).
+
+    The deep levels (C_out >= 4 * base_channels: 256 and 512 channels in unet64, a quarter of the step and bound by the
+    tensor pipe under bf16x3) run ONE fp16 product per tap; everything else keeps the bf16 hi/lo split.  Measured: a whole
+    UNet forward with this rule differs from the fp32 oracle by 6e-5 (tools/precision_study.py; bf16x3 everywhere: 1.5e-5)
+    against the 1e-3 the north star allows.  VQVS_PREC=bf16x3 | f16 forces one format everywhere (study / tests)."""
+    forced = os.environ.get("VQVS_PREC")
+    if forced:
+        return {"bf16x3": L.PREC_BF16X3, "f16": L.PREC_F16}[forced]
+    if base_channels is not None and c_out >= 4 * base_channels:
+        return L.PREC_F16
+    return L.PREC_BF16X3
+
+
+def _pack(conv: torch.nn.Conv1d, skip: Optional[torch.nn.Conv1d], prec: int = L.PREC_BF16X3) -> Optional[Packed]:
     lib = L.load()
     c_out, c_in, k = conv.weight.shape
     c_skip = skip.weight.shape[1] if skip is not None else 0
-    nbytes = lib.vqvs_packed_weight_bytes(c_out, c_in, k, c_skip)
+    nbytes = lib.vqvs_packed_weight_bytes(c_out, c_in, k, c_skip, prec)
     if nbytes <= 0:
         return None
     img = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
     w = _f32(conv.weight)
     ws = _f32(skip.weight) if skip is not None else None
-    L.check(lib.vqvs_pack_conv_weights(L.ptr(w), L.ptr(ws), c_out, c_in, k, c_skip, L.ptr(img), L.stream_ptr()),
+    L.check(lib.vqvs_pack_conv_weights(L.ptr(w), L.ptr(ws), c_out, c_in, k, c_skip, prec, L.ptr(img), L.stream_ptr()),
             "vqvs_pack_conv_weights")
     torch.cuda.current_stream().synchronize()  # w / ws temporaries may be freed after this
-    return img
+    return Packed(img, prec)
 
 
 def _skip_proj(block):
@@ -202,20 +224,26 @@ def _tail_conv(block):
     return block.post_cond[len(block.post_cond) - 1]
 
 
-def weights_for(net, blocks: Sequence, backend: str) -> Weights:
-    """(Re)build the derived weight images of `net` when any parameter changed."""
+def weights_for(net, blocks: Sequence, backend: str, reduced_precision: bool = False) -> Weights:
+    """(Re)build the derived weight images of `net` when any parameter changed.
+
+    reduced_precision: apply conv_precision()'s per-level rule (the predictor and the guidance stem; the VQ-VAE encoder
+    keeps bf16x3 everywhere because its outputs decide code indices)."""
     sig = _signature(net)
     w = getattr(net, "_vqvs_weights", None)
-    if w is not None and w.signature == (sig, backend):
+    key = (sig, backend, reduced_precision, os.environ.get("VQVS_PREC"))
+    if w is not None and w.signature == key:
         return w
     w = Weights()
-    w.signature = (sig, backend)
+    w.signature = key
     device = next(net.parameters()).device
+    bc = getattr(net, "base_channels", None) if reduced_precision else None
     with torch.no_grad():
         if backend == "umma":
             for blk in blocks:
-                w.packed[(id(blk), 1)] = _pack(blk.pre_cond[2], None)
-                w.packed[(id(blk), 2)] = _pack(_tail_conv(blk), _skip_proj(blk))
+                prec = conv_precision(blk.out_channels, bc)
+                w.packed[(id(blk), 1)] = _pack(blk.pre_cond[2], None, prec)
+                w.packed[(id(blk), 2)] = _pack(_tail_conv(blk), _skip_proj(blk), prec)
             for name in ("cond_proj",):
                 conv = getattr(net, name, None)
                 if isinstance(conv, torch.nn.Conv1d):
@@ -298,8 +326,10 @@ def _emit_conv(plan: Plan, srcs: List[Act], conv: torch.nn.Conv1d, out: Act, *, 
         d.sa, d.sb = skip_srcs[0].ptr, (skip_srcs[1].ptr if len(skip_srcs) > 1 else 0)
         if skip_proj is not None:
             d.w_skip, d.b_skip = L.ptr(skip_proj.weight), L.ptr(skip_proj.bias)
-    d.w_packed = L.ptr(packed)
+    d.w_packed = L.ptr(packed.img) if packed is not None else 0
     d.reserved_ = int(os.environ.get("VQVS_DEBUG_FLAGS", "0"))  # kernel ablation switches (profiling only)
+    if packed is not None:
+        d.reserved_ |= packed.prec << L.CONV_PREC_SHIFT
     d.out, d.stats_out = out.ptr, out.stats_ptr
     out.producer = d
     plan.produced.append(out)
@@ -378,7 +408,7 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
         raise ValueError("the CUDA predictor path implements in_channels == 1 (waveforms)")
     device = next(net.parameters()).device
     blocks = _predictor_blocks(net)
-    w = weights_for(net, blocks, backend)
+    w = weights_for(net, blocks, backend, reduced_precision=True)
     plan = Plan(device, batch, backend)
     plan.weights = w
     bc = net.base_channels

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 RESIZE_NONE, RESIZE_DOWN2, RESIZE_UP2 = 0, 1, 2
 SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
@@ -18,6 +18,8 @@ OP_CONV_SIMT, OP_CONV_UMMA, OP_GN_FINALIZE, OP_CONV_IN, OP_CONV_OUT = 1, 2, 3, 4
 OP_TIME_EMBED, OP_FILM, OP_MEMSET, OP_DDPM_FINISH = 6, 7, 8, 9
 CONV_PAIR_STATS = 1024  # VqvsConv.reserved_ flag
 CONV_STAT_GRAN_SHIFT = 12  # bits 12..15 of VqvsConv.reserved_: log2 of the statistics granularity
+CONV_PREC_SHIFT = 16  # bits 16..17 of VqvsConv.reserved_: tensor-core operand format
+PREC_BF16X3, PREC_F16 = 0, 1
 
 _i32, _i64, _p = C.c_int32, C.c_int64, C.c_void_p
 
@@ -93,8 +95,8 @@ SIGNATURES = {
     "vqvs_conv1d_fused": (C.c_int, [C.POINTER(Conv), _p]),
     "vqvs_conv1d_umma": (C.c_int, [C.POINTER(Conv), _p]),
     "vqvs_conv1d_umma_supported": (C.c_int, [C.POINTER(Conv)]),
-    "vqvs_packed_weight_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "vqvs_pack_conv_weights": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "vqvs_packed_weight_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vqvs_pack_conv_weights": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_gn_finalize": (C.c_int, [C.POINTER(GnFinalize), _p]),
     "vqvs_channel_stats": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_conv_in": (C.c_int, [C.POINTER(ConvIn), _p]),
