@@ -224,6 +224,14 @@ int vqvs_ddpm_x0_sum(const float* x_t, const float* eps, const float* coef, int 
                      double* x0_sum, void* stream);
 
 /*
+ * Standard-normal noise keyed by (seed, GLOBAL sample index, step) for batch-sharded sampling: out[r, :]
+ * (rows of `length` floats) depends only on (seed, first_row + r, step) -- Philox4x32-10 + Box-Muller on the device.
+ * It replaces the reference's `torch.randn_like(x_t)` (diffusion/diffusion.py:62-63) where the result must not depend
+ * on how a batch is split over GPUs; step = -1 is used for x_T.
+ */
+int vqvs_keyed_normal(float* out, int rows, int64_t length, uint64_t seed, int64_t first_row, int32_t step, void* stream);
+
+/*
  * Timestep embedding (models/wavegrad.py:359-373, models/unet.py:40-45,133-135):
  *   e = [cos(t*f) | sin(t*f)];  emb = W2*GELU(W1*e + b1) + b2 (+ class_embed[label])
  * writes emb and GELU(emb) (the input of every FiLM Linear, unet.py:274-278).

@@ -10,9 +10,8 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--bc", type=int, default=64)
 ap.add_argument("--t", type=int, default=64000)
 a = ap.parse_args()
-bench.BASE_CHANNELS = a.bc
 dev = torch.device("cuda:0")
-model = bench.build_model(dev)
+model = bench.build_model(dev, a.bc)
 x = torch.randn(a.batch, 1, a.t, device=dev)
 plan, per_op, by_kind, umma = bench.profile_kernels(model, x)
 alg = bench.conv_algorithmic_bytes(plan)

@@ -423,14 +423,68 @@ __global__ void __launch_bounds__(VQ_THREADS) vq_argmin_kernel(const float* __re
 }
 
 __global__ void vq_embed_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dict, int n, int c,
-                                int t1, float* __restrict__ out) {
+                                int t1, int d, float* __restrict__ out) {
   const size_t total = (size_t)n * c * t1;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int t = (int)(i % t1);
     const size_t nc = i / t1;
     const int ch = (int)(nc % c);
     const int b = (int)(nc / c);
-    out[i] = dict[(size_t)idx[(size_t)b * t1 + t] * c + ch];
+    // F.embedding raises on an out-of-range code; a kernel cannot, so it never reads outside the dictionary and marks the
+    // element NaN (the Python wrapper checks the range up front and raises IndexError like the reference)
+    const int64_t code = idx[(size_t)b * t1 + t];
+    out[i] = (code >= 0 && code < d) ? dict[(size_t)code * c + ch] : __int_as_float(0x7fc00000);
+  }
+}
+
+// =============================================================================
+// keyed Gaussian noise (sharding-invariant sampling)
+// =============================================================================
+// out[r, j] ~ N(0, 1) as a pure function of (seed, first_row + r, step, j): Philox4x32-10 with key = seed and counter =
+// (global row, step, j / 4); the four 32-bit words become two Box-Muller pairs.  A batch therefore draws the same noise
+// however it is sharded over GPUs, with no host RNG, no H2D copy and no dependence on the device generator's state.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* o) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__global__ void keyed_normal_kernel(float* __restrict__ out, int rows, long long length, unsigned long long seed,
+                                    long long first_row, int step) {
+  const long long quads = (length + 3) / 4;
+  const long long total = (long long)rows * quads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / quads);
+    const long long q = i - (long long)r * quads;
+    const unsigned long long row = (unsigned long long)(first_row + r);
+    uint32_t w[4];
+    philox4x32_10((uint32_t)row, (uint32_t)(row >> 32) ^ ((uint32_t)step * 0x85EBCA6Bu), (uint32_t)q, (uint32_t)(q >> 32) + (uint32_t)step,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    float z[4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float u1 = ((float)(w[2 * p] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+      const float u2 = ((float)(w[2 * p + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincosf(6.283185307179586f * u2, &sn, &cs);
+      z[2 * p] = rad * cs;
+      z[2 * p + 1] = rad * sn;
+    }
+    float* dst = out + (long long)r * length + 4 * q;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * q + e < length) dst[e] = z[e];
   }
 }
 
@@ -736,8 +790,20 @@ extern "C" int vqvs_vq_embed(const int64_t* idx, const float* dict, int n, int c
   VQVS_CHECK_ARG(idx && dict && out && n > 0 && c > 0 && t1 > 0 && d > 0, "vq_embed: bad arguments");
   const size_t total = (size_t)n * c * t1;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  vq_embed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, dict, n, c, t1, out);
+  vq_embed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, dict, n, c, t1, d, out);
   VQVS_CHECK_LAUNCH("vqvs_vq_embed");
+  return VQVS_OK;
+}
+
+extern "C" int vqvs_keyed_normal(float* out, int rows, int64_t length, uint64_t seed, int64_t first_row, int32_t step,
+                                 void* stream) {
+  VQVS_CHECK_ARG(rows >= 0 && length >= 0 && (out || rows == 0 || length == 0), "keyed_normal: bad arguments");
+  if (rows == 0 || length == 0) return VQVS_OK;
+  const long long total = (long long)rows * ((length + 3) / 4);
+  const int blocks = (int)(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+  keyed_normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, rows, (long long)length, (unsigned long long)seed,
+                                                               (long long)first_row, (int)step);
+  VQVS_CHECK_LAUNCH("vqvs_keyed_normal");
   return VQVS_OK;
 }
 

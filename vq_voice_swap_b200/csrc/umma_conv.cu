@@ -1686,7 +1686,11 @@ cudaError_t read_prof(unsigned long long* host32);
 #ifdef VQVS_KIND_TU
 template <int KIND>
 static cudaError_t launch_kind_impl(VQVS_LAUNCHER_ARGS) {
-  static bool attr_done = false;
+  // per DEVICE: the opt-in shared-memory size is an attribute of the function in the current device's context
+  static bool attr_done_dev[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  bool& attr_done = attr_done_dev[dev];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<1, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess && KIND != 3)
@@ -1847,6 +1851,26 @@ using vqvs::umma::Geo;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// (compute capability, SM count) of the CURRENT device, cached per device ordinal (one process may drive several GPUs)
+static int device_props(int* cc, int* sms) {
+  static int cached_cc[64] = {}, cached_sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    (void)cudaGetLastError();
+    return vqvs_device_info(cc, sms);
+  }
+  if (!cached_sms[dev]) {
+    int c = 0, s = 0;
+    const int rc = vqvs_device_info(&c, &s);
+    if (rc != VQVS_OK) return rc;
+    cached_cc[dev] = c;
+    cached_sms[dev] = s;
+  }
+  *cc = cached_cc[dev];
+  *sms = cached_sms[dev];
+  return VQVS_OK;
+}
+
 // TMA needs 16-B aligned bases and row pitches (length % 4 == 0); otherwise the kernel reads directly.
 static bool tma_eligible(const VqvsConv* d) {
   if (d->t_in % 4 || !aligned16(d->xa) || (d->c_b && !aligned16(d->xb))) return false;
@@ -1872,11 +1896,8 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
     // Two time tiles per work item halve the weight streaming, but (measured, tools/prof_roles.py with VQVS_FORCE_MT)
     // single tiles win when the epilogue also fetches an identity skip, and when the coarser items waste >= 10 % of
     // the last round of the persistent schedule.
-    static int sms = 0;
-    if (!sms) {
-      int cc = 0;
-      if (vqvs_device_info(&cc, &sms) != VQVS_OK || sms <= 0) sms = 148;
-    }
+    int sms = 0, cc = 0;
+    if (device_props(&cc, &sms) != VQVS_OK || sms <= 0) sms = 148;
     const long long per = (long long)g->n_tiles * d->batch;
     const long long items2 = per * ceil_div(d->t_out, 2 * umma::TILE_M), items1 = per * ceil_div(d->t_out, umma::TILE_M);
     const long long rounds2 = 2 * ((items2 + sms - 1) / sms), rounds1 = (items1 + sms - 1) / sms;
@@ -1914,12 +1935,8 @@ extern "C" int vqvs_pack_conv_weights(const float* w, const float* w_skip, int c
 }
 
 static int require_sm100() {
-  static int cc = -1;
-  if (cc < 0) {
-    int c = 0, sms = 0;
-    if (vqvs_device_info(&c, &sms) != VQVS_OK) return VQVS_ECUDA;
-    cc = c;
-  }
+  int cc = 0, sms = 0;
+  if (device_props(&cc, &sms) != VQVS_OK) return VQVS_ECUDA;
   if (cc / 10 != 10) {
     set_error("tcgen05 path needs an sm_100-class device, found sm_%d", cc);
     return VQVS_EARCH;
@@ -2002,11 +2019,8 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
       if (d->s_b && (rc = encode_map(&maps[3], d->sb, d->batch * d->s_b, d->t_skip, g.skip_box_w))) return rc;
     }
   }
-  static int sm_count = 0;
-  if (!sm_count) {
-    int cc = 0;
-    if (vqvs_device_info(&cc, &sm_count) != VQVS_OK) return VQVS_ECUDA;
-  }
+  int sm_count = 0, cc_unused = 0;
+  if (device_props(&cc_unused, &sm_count) != VQVS_OK) return VQVS_ECUDA;
   g.tiles_t = ceil_div(d->t_out, umma::TILE_M * g.mt);  // work items along time (mt tiles each)
   g.tiles_total = g.tiles_t * g.n_tiles * d->batch;
   int grid = sm_count < g.tiles_total ? sm_count : g.tiles_total;

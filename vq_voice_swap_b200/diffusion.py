@@ -108,8 +108,18 @@ class Diffusion:
             mean = mean + _per_sample(co["sig2"], x_t) * cond_fn(mean, ts - step)
             eps = (-mean * _per_sample(co["alpha"].sqrt(), x_t) + x_t) * _per_sample((1 - co["ab_t"]).sqrt(), x_t)
             eps = (eps / _per_sample(co["beta"], x_t)).contiguous()
-        x0_sum = engine.ddpm_x0_sum(x_t, eps, coef) if constrain else None
-        return engine.ddpm_finish(x_t, eps, coef, noise, out, x0_sum)
+        if not constrain:
+            return engine.ddpm_finish(x_t, eps, coef, noise, out, None)
+        # constrain subtracts the mean over the LAST axis only (reference diffusion.py:87: x0.mean(dim=-1, keepdim=True)),
+        # i.e. per (sample, channel) row: run the row kernels over [N*C] rows of length T with the coefficients repeated
+        n, t = x_t.shape[0], x_t.shape[-1]
+        rows = x_t[0].numel() // t
+        if rows > 1:
+            coef = coef.repeat_interleave(rows, dim=0).contiguous()
+        view = lambda a: None if a is None else a.reshape(n * rows, 1, t)  # noqa: E731
+        x0_sum = engine.ddpm_x0_sum(view(x_t), view(eps), coef)
+        engine.ddpm_finish(view(x_t), view(eps), coef, view(noise), view(out), x0_sum)
+        return out
 
     def ddpm_previous(self, x_t, ts, step, epsilon_prediction, noise=None, sigma_large=False, constrain=False,
                       cond_fn: Callable = None):
@@ -118,17 +128,25 @@ class Diffusion:
         if noise is None:
             noise = torch.randn_like(x_t)
         with torch.no_grad():
+            dtype = x_t.dtype
             x_t, eps = engine._f32(x_t), engine._f32(epsilon_prediction)
             ts = ts.to(x_t)
             co = self.step_coefficients(ts, step, sigma_large)
-            return self._update(x_t, ts, step, eps, engine._f32(noise), co, constrain, cond_fn)
+            return self._update(x_t, ts, step, eps, engine._f32(noise), co, constrain, cond_fn).to(dtype)
 
     # -- sampler ----------------------------------------------------------------------------
     def ddpm_sample(self, x_T, predictor, steps: int, progress: bool = False, sigma_large: bool = False,
-                    constrain: bool = False, cond_fn: Callable = None, schedule: Callable = None):
-        """Run `steps` reverse-diffusion steps from x_T (reference diffusion.py:92-133)."""
+                    constrain: bool = False, cond_fn: Callable = None, schedule: Callable = None,
+                    noise_fn: Optional[Callable] = None):
+        """Run `steps` reverse-diffusion steps from x_T (reference diffusion.py:92-133).
+
+        noise_fn(step_index, like) -> noise tensor replaces the reference's `torch.randn_like(x_t)` draw of a step (an
+        extension used by sharding.sample_sharded for noise keyed by the global sample index); by default the device
+        generator is consumed exactly like the reference: one randn_like per step except the last."""
         engine._require_cuda(x_T)
         fast = engine.resolve_predictor(predictor)
+        if fast is not None and fast[0].training and any(getattr(m, "dropout", 0.0) for m in fast[0].modules()):
+            raise RuntimeError("dropout > 0 in train mode is not implemented on the sm_100a path: call model.eval()")
         x_t = engine._f32(x_T)
         bufs = [torch.empty_like(x_t), torch.empty_like(x_t)]
         grid = [(i + 1) / steps for i in range(steps)]
@@ -138,22 +156,29 @@ class Diffusion:
             from tqdm.auto import tqdm
 
             its = tqdm(its)
+
+        def draw(i):
+            if i + 1 == steps:
+                return None  # zeros on the last step (:127)
+            return torch.randn_like(x_t) if noise_fn is None else engine._f32(noise_fn(i, x_t))
+
         for i, t in its:
             ts = torch.tensor([t] * x_T.shape[0]).to(x_t)
             if schedule is not None:
                 t_step = schedule(ts) - schedule(ts - 1 / steps)
                 ts = schedule(ts)
             with torch.no_grad():
-                last = i + 1 == steps
-                noise = None if last else torch.randn_like(x_t)  # zeros on the last step (:127)
                 co = self.step_coefficients(ts, t_step, sigma_large)
                 out = bufs[i & 1]
                 if fast is not None:
+                    # our predictor consumes no random numbers, so drawing the noise first keeps the generator sequence of
+                    # the reference (which draws after the predictor call, :120-131) and lets the last kernel apply it
+                    noise = draw(i)
                     net, cond, labels = fast
                     res = engine.fused_sample_step(net, x_t, ts, cond, labels, co["packed"], noise, out,
                                                    constrain, cond_fn is not None, first=(i == 0))
                     x_t = self._update(x_t, ts, t_step, res, noise, co, constrain, cond_fn, out) if cond_fn else res
                 else:
                     eps = engine._f32(predictor(x_t, ts))
-                    x_t = self._update(x_t, ts, t_step, eps, noise, co, constrain, cond_fn, out)
-        return x_t.clone()
+                    x_t = self._update(x_t, ts, t_step, eps, draw(i), co, constrain, cond_fn, out)
+        return x_t.clone().to(x_T.dtype)

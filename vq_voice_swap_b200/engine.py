@@ -78,7 +78,30 @@ class PlanCache:
 
 
 def _signature(module: torch.nn.Module):
+    """(pointer, version) of every parameter: plans and packed weight images are rebuilt when it changes.  In-place
+    updates that bypass autograd's version counter (`p.data.mul_()`) are invisible here: call invalidate(module)."""
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def invalidate(module: torch.nn.Module) -> None:
+    """Drop every compiled plan and derived weight image of `module` (after editing parameters through `.data`)."""
+    for m in module.modules():
+        plans = getattr(m, "_plans", None)
+        if isinstance(plans, PlanCache):
+            plans.clear()
+            plans.signature = None
+        if hasattr(m, "_vqvs_weights"):
+            m._vqvs_weights = None
+
+
+def _check_module(net: torch.nn.Module) -> None:
+    """Plans embed raw parameter pointers that the kernels read as dense fp32: refuse anything else loudly."""
+    for name, p in net.named_parameters():
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise TypeError(f"parameter {name} is {p.dtype}{'' if p.is_contiguous() else ', non-contiguous'}: the sm_100a path "
+                            "needs contiguous float32 parameters (no .half()/.double() models)")
+    if net.training and any(getattr(m, "dropout", 0.0) for m in net.modules()):
+        raise RuntimeError("dropout > 0 in train mode is not implemented on the sm_100a path (sampling only): call .eval()")
 
 
 def _require_cuda(*tensors):
@@ -162,7 +185,9 @@ class Plan:
         return self
 
     def run(self):
-        L.check(L.load().vqvs_run(self.ops, len(self.descs), L.stream_ptr()), "vqvs_run")
+        # the launches go to the plan's device and to torch's current stream ON THAT DEVICE, whatever device is current
+        with torch.cuda.device(self.device):
+            L.check(L.load().vqvs_run(self.ops, len(self.descs), L.stream_ptr(self.device)), "vqvs_run")
 
 
 class Weights:
@@ -209,9 +234,11 @@ def _pack(conv: torch.nn.Conv1d, skip: Optional[torch.nn.Conv1d], prec: int = L.
     img = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
     w = _f32(conv.weight)
     ws = _f32(skip.weight) if skip is not None else None
-    L.check(lib.vqvs_pack_conv_weights(L.ptr(w), L.ptr(ws), c_out, c_in, k, c_skip, prec, L.ptr(img), L.stream_ptr()),
-            "vqvs_pack_conv_weights")
-    torch.cuda.current_stream().synchronize()  # w / ws temporaries may be freed after this
+    dev = conv.weight.device
+    with torch.cuda.device(dev):
+        L.check(lib.vqvs_pack_conv_weights(L.ptr(w), L.ptr(ws), c_out, c_in, k, c_skip, prec, L.ptr(img), L.stream_ptr(dev)),
+                "vqvs_pack_conv_weights")
+        torch.cuda.current_stream(dev).synchronize()  # w / ws temporaries may be freed after this
     return Packed(img, prec)
 
 
@@ -407,6 +434,7 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
     if net.in_channels != 1:
         raise ValueError("the CUDA predictor path implements in_channels == 1 (waveforms)")
     device = next(net.parameters()).device
+    _check_module(net)
     blocks = _predictor_blocks(net)
     w = weights_for(net, blocks, backend, reduced_precision=True)
     plan = Plan(device, batch, backend)
@@ -527,8 +555,25 @@ def _check_input(x, channels: int):
         raise ValueError(f"expected an [N x {channels} x T] tensor, got {tuple(x.shape)}")
 
 
+def check_predictor_inputs(net, x, cond, labels):
+    """The argument contract of reference models/unet.py:126-131 plus the shape / range checks the reference gets for
+    free from nn.Embedding and Conv1d (both raise on a bad label or channel count)."""
+    assert (labels is None) == (net.num_labels is None), "must provide labels if and only if model is class conditional"
+    assert (cond is None) == (net.cond_channels is None), "must provide cond sequence if and only if model is conditional"
+    batch = x.shape[0]
+    if labels is not None:
+        if labels.dtype not in (torch.int64, torch.int32) or labels.numel() != batch:
+            raise ValueError(f"labels must be {batch} integers, got {tuple(labels.shape)} {labels.dtype}")
+        lo, hi = int(labels.min()), int(labels.max())
+        if lo < 0 or hi >= net.num_labels:
+            raise IndexError(f"label out of range: [{lo}, {hi}] with num_labels = {net.num_labels}")
+    if cond is not None and (cond.dim() != 3 or cond.shape[0] != batch or cond.shape[1] != net.cond_channels):
+        raise ValueError(f"cond must be [{batch} x {net.cond_channels} x T1], got {tuple(cond.shape)}")
+
+
 def stage_predictor_inputs(net, plan: Plan, x, ts, cond, labels):
     """Point the program at this call's inputs (no copies for x; tiny copies for ts/labels/cond)."""
+    check_predictor_inputs(net, x, cond, labels)
     plan.x_in = _f32(x)  # kept alive until the next call
     plan.slots["conv_in"].x = plan.x_in.data_ptr()
     plan.ts.copy_(ts.to(device=plan.device, dtype=torch.float32).reshape(-1).expand(plan.batch), non_blocking=True)
@@ -561,6 +606,7 @@ def build_encoder_plan(net, batch: int, t: int, backend: str) -> Plan:
     if net.in_channels != 1:
         raise ValueError("the CUDA encoder path implements in_channels == 1 (waveforms)")
     device = next(net.parameters()).device
+    _check_module(net)
     blocks = list(net.blocks)
     w = weights_for(net, blocks, backend)
     plan = Plan(device, batch, backend)
@@ -636,9 +682,9 @@ def run_single_block(blk, x, emb) -> torch.Tensor:
                     getattr(plan, "ab", None))
         return plan.compile()
 
-    with torch.no_grad():
-        plan = blk._plans.get((batch, t, x.device.index, backend), _signature(blk), build)
-        stream = L.stream_ptr()
+    with torch.no_grad(), torch.cuda.device(x.device):
+        plan = blk._plans.get((batch, t, x.device.index, backend, os.environ.get("VQVS_PREC")), _signature(blk), build)
+        stream = L.stream_ptr(x.device)
         plan.arena.zero_()
         plan.src.buf.copy_(x)
         L.check(lib.vqvs_channel_stats(plan.src.ptr, batch, c, t, plan.src.stats_ptr, stream), "vqvs_channel_stats")
@@ -697,14 +743,16 @@ def ddpm_finish(x_t, eps, coef, noise, out, x0_sum=None):
     d.use_x0_mean = 1 if x0_sum is not None else 0
     d.x_t, d.eps, d.noise, d.coef = x_t.data_ptr(), eps.data_ptr(), L.ptr(noise), coef.data_ptr()
     d.x0_sum, d.out = L.ptr(x0_sum), out.data_ptr()
-    L.check(L.load().vqvs_ddpm_finish(C.byref(d), L.stream_ptr()), "vqvs_ddpm_finish")
+    with torch.cuda.device(x_t.device):
+        L.check(L.load().vqvs_ddpm_finish(C.byref(d), L.stream_ptr(x_t.device)), "vqvs_ddpm_finish")
     return out
 
 
 def ddpm_x0_sum(x_t, eps, coef):
     s = torch.zeros(x_t.shape[0], dtype=torch.float64, device=x_t.device)
-    L.check(L.load().vqvs_ddpm_x0_sum(x_t.data_ptr(), eps.data_ptr(), coef.data_ptr(), x_t.shape[0], x_t[0].numel(),
-                                      s.data_ptr(), L.stream_ptr()), "vqvs_ddpm_x0_sum")
+    with torch.cuda.device(x_t.device):
+        L.check(L.load().vqvs_ddpm_x0_sum(x_t.data_ptr(), eps.data_ptr(), coef.data_ptr(), x_t.shape[0], x_t[0].numel(),
+                                          s.data_ptr(), L.stream_ptr(x_t.device)), "vqvs_ddpm_x0_sum")
     return s
 
 

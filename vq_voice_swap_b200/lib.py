@@ -108,6 +108,7 @@ SIGNATURES = {
     "vqvs_film_linear": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_vq_argmin": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_vq_embed": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "vqvs_keyed_normal": (C.c_int, [_p, C.c_int, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, _p]),
     "vqvs_run": (C.c_int, [C.POINTER(Op), C.c_int, _p]),
     "vqvs_run_timed": (C.c_int, [C.POINTER(Op), C.c_int, _p, C.POINTER(C.c_float)]),
     "vqvs_launch_counts": (C.c_int, [C.POINTER(C.c_uint64)]),
@@ -159,10 +160,11 @@ def launch_counts() -> dict:
     return {name: int(buf[kind]) for kind, name in OP_NAMES.items()}
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """torch's current CUDA stream on `device` (default: the current device) as a cudaStream_t."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def ptr(t) -> int:

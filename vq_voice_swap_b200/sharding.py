@@ -3,15 +3,17 @@
 Every op on the sampling path is per-sample (GroupNorm normalises inside a sample; `constrain`
 averages over time inside a sample), so a batch splits across GPUs with NO data-path collective:
 rank r owns samples [lo, hi), replicas hold the same weights, and one all_gather re-assembles the
-finished waveforms.  Noise is keyed by (seed, GLOBAL sample index, step), so the result does not
-depend on how many GPUs shared the work.
+finished waveforms.  Noise is keyed by (seed, GLOBAL sample index, step) and drawn on the device
+(vqvs_keyed_normal: Philox4x32-10 + Box-Muller), so the result does not depend on how many GPUs
+shared the work and costs no host RNG or H2D copy.
 """
 
-import hashlib
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import lib as L
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -23,24 +25,20 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _seed_for(seed: int, index: int, step: int) -> int:
-    h = hashlib.blake2b(f"{seed}/{index}/{step}".encode(), digest_size=8).digest()
-    return int.from_bytes(h, "little") & 0x7FFFFFFFFFFFFFFF
-
-
-def keyed_noise(seed: int, indices: range, step: int, length: int, device="cpu") -> torch.Tensor:
-    """[len(indices), 1, length] standard normal noise; row i depends only on (seed, indices[i], step)."""
-    rows = []
-    for idx in indices:
-        gen = torch.Generator(device="cpu")
-        gen.manual_seed(_seed_for(seed, idx, step))
-        rows.append(torch.randn(1, length, generator=gen))
-    out = torch.stack(rows) if rows else torch.empty(0, 1, length)
-    return out.to(device)
+def keyed_noise(seed: int, first_index: int, count: int, step: int, length: int, device) -> torch.Tensor:
+    """[count, 1, length] standard-normal noise on `device`; row i depends only on (seed, first_index + i, step)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("keyed_noise draws on the GPU (vqvs_keyed_normal); there is no CPU fallback")
+    out = torch.empty(count, 1, length, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        L.check(L.load().vqvs_keyed_normal(out.data_ptr(), count, length, seed & 0xFFFFFFFFFFFFFFFF, first_index, step,
+                                           L.stream_ptr(device)), "vqvs_keyed_normal")
+    return out
 
 
 def gather_samples(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """all_gather the per-rank shards (possibly of unequal length) back into the [total, ...] batch."""
+    """all_gather the per-rank shards (possibly of unequal or zero length) back into the [total, ...] batch."""
     if not dist.is_available() or not dist.is_initialized():
         return local
     world = dist.get_world_size(group)
@@ -54,27 +52,29 @@ def gather_samples(local: torch.Tensor, total: int, group: Optional[dist.Process
     return torch.cat([p[: hi - lo] for p, (lo, hi) in zip(parts, sizes)])
 
 
-def sample_sharded(model, total: int, steps: int, seed: int, length: int = 64000, device=None, **kwargs) -> torch.Tensor:
+def sample_sharded(model, total: int, steps: int, seed: int, length: int = 64000, device=None,
+                   labels: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
     """Draw `total` samples with the batch split over the ranks of the default process group.
 
-    x_T and every step's noise are keyed by the global sample index; returns the full batch on every rank.
-    """
+    x_T and every step's noise are keyed by the global sample index; `labels` / `cond` (for conditional models) are given
+    for the WHOLE batch and sliced per rank.  A rank whose shard is empty (total < world size) skips sampling but still
+    joins the all_gather.  Returns the full batch on every rank."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(total, rank, world)
-    device = device or next(model.parameters()).device
-    x_T = keyed_noise(seed, range(lo, hi), -1, length, device)
-    step = [0]
-    orig = torch.randn_like
+    device = torch.device(device or next(model.parameters()).device)
+    if hi > lo:
+        from .engine import BoundPredictor
 
-    def keyed_like(x, **kw):  # the sampler asks for one noise tensor per step (reference diffusion.py:62-63)
-        t = keyed_noise(seed, range(lo, hi), step[0], length, x.device).to(x.dtype)
-        step[0] += 1
-        return t
-
-    torch.randn_like = keyed_like
-    try:
-        local = model.diffusion.ddpm_sample(x_T, model.predictor, steps, **kwargs)
-    finally:
-        torch.randn_like = orig
+        x_T = keyed_noise(seed, lo, hi - lo, -1, length, device)
+        bound = {}
+        if labels is not None:
+            bound["labels"] = labels[lo:hi].to(device)
+        if cond is not None:
+            bound["cond"] = cond[lo:hi].to(device)
+        predictor = BoundPredictor(model.predictor, **bound) if bound else model.predictor
+        local = model.diffusion.ddpm_sample(
+            x_T, predictor, steps, noise_fn=lambda i, like: keyed_noise(seed, lo, hi - lo, i, length, like.device), **kwargs)
+    else:
+        local = torch.empty(0, 1, length, device=device)
     return gather_samples(local, total)

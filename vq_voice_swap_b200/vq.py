@@ -29,10 +29,15 @@ class VQ(nn.Module):
         engine._require_cuda(idxs, self.dictionary)
         n = idxs.shape[0]
         flat = idxs.reshape(n, -1).to(torch.int64).contiguous()
+        if flat.numel():
+            lo, hi = int(flat.min()), int(flat.max())
+            if lo < 0 or hi >= self.num_codes:  # F.embedding (reference vq.py:108) raises the same way
+                raise IndexError(f"code index out of range: [{lo}, {hi}] with a dictionary of {self.num_codes}")
         out = torch.empty(n, self.num_channels, flat.shape[1], device=idxs.device, dtype=torch.float32)
         d = engine._f32(self.dictionary)
-        L.check(L.load().vqvs_vq_embed(flat.data_ptr(), d.data_ptr(), n, self.num_channels, flat.shape[1],
-                                       self.num_codes, out.data_ptr(), L.stream_ptr()), "vqvs_vq_embed")
+        with torch.cuda.device(idxs.device):
+            L.check(L.load().vqvs_vq_embed(flat.data_ptr(), d.data_ptr(), n, self.num_channels, flat.shape[1],
+                                           self.num_codes, out.data_ptr(), L.stream_ptr(idxs.device)), "vqvs_vq_embed")
         return out.reshape(n, self.num_channels, *idxs.shape[1:])
 
     def forward(self, inputs: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -46,8 +51,9 @@ class VQ(nn.Module):
             t1 = x.shape[2]
             idxs = torch.empty(n, t1, device=x.device, dtype=torch.int64)
             d = engine._f32(self.dictionary)
-            L.check(L.load().vqvs_vq_argmin(x.data_ptr(), d.data_ptr(), n, self.num_channels, t1, self.num_codes,
-                                            idxs.data_ptr(), L.stream_ptr()), "vqvs_vq_argmin")
+            with torch.cuda.device(x.device):
+                L.check(L.load().vqvs_vq_argmin(x.data_ptr(), d.data_ptr(), n, self.num_channels, t1, self.num_codes,
+                                                idxs.data_ptr(), L.stream_ptr(x.device)), "vqvs_vq_argmin")
             idxs = idxs.reshape(n, *inputs.shape[2:])
             embedded = self.embed(idxs)
             if self.training:
