@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 3
+#define VQVS_ABI_VERSION 4
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -223,6 +223,71 @@ int vqvs_ddpm_finish(const VqvsDdpmFinish* d, void* stream);
 int vqvs_ddpm_x0_sum(const float* x_t, const float* eps, const float* coef, int batch, int t,
                      double* x0_sum, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Classifier guidance (BASELINE configs[4]): reference models/classifier.py:18-191 evaluated forward AND backward
+ * (input gradient only) without ATen/autograd -- sample_diffusion.py:34-42 needs d log p(label | x_t, t) / d x_t.
+ * The stem's convolutions, including the transposed ("dgrad") ones, are vqvs_conv1d_umma launches; these ops are the
+ * pieces between them.  A GroupNorm(+FiLM) followed by GELU, v = gelu(z*S + H), is differentiated in three steps that
+ * mirror the forward's producer-statistics / consumer-finalize split:
+ *   vqvs_gn_bwd_prep      prep = [S | H | mean | rstd | gf] per (n, c) from the forward's statistics (gf = gamma*(1+a))
+ *   vqvs_gelu_bwd         q = d_in * gelu'(z*S + H) * gf;  acc[n,c] += (sum_t q, sum_t q*zhat),  zhat = (z-mean)*rstd
+ *   vqvs_gn_bwd_finalize  coef = [A | B | C] with dz = A*q + B*z + C = rstd*(q - mean_g(q) - zhat*mean_g(q*zhat))
+ *   vqvs_affine3          out = A*q + B*z + C (+ add), add = the skip path's gradient (optionally through avg_pool^T)
+ */
+typedef struct VqvsGnBwdPrep { const VqvsGnFinalize* gn; float* prep; /* [5][batch*C] */ } VqvsGnBwdPrep;
+int vqvs_gn_bwd_prep(const VqvsGnFinalize* d, float* prep, void* stream);
+typedef struct VqvsGeluBwd {
+  int32_t batch, c, t, up;   /* up = 1: d_in is [batch,c,t/2] and reaches position i as 0.5*d_in[i/2] (avg_pool1d backward) */
+  const float* d_in; const float* z; const float* prep;
+  float* q;                  /* [batch,c,t] */
+  double* acc;               /* [batch,c,2], zeroed by the caller */
+} VqvsGeluBwd;
+int vqvs_gelu_bwd(const VqvsGeluBwd* d, void* stream);
+typedef struct VqvsGnBwdFinalize {
+  int32_t batch, c, groups, pad_;
+  int64_t count;             /* positions per channel */
+  const double* acc; const float* prep;
+  float* coef;               /* [3][batch*c] */
+} VqvsGnBwdFinalize;
+int vqvs_gn_bwd_finalize(const VqvsGnBwdFinalize* d, void* stream);
+typedef struct VqvsAffine3 {
+  int32_t batch, c, t, add_mode;  /* 0: no add, 1: + add[i], 2: + 0.5*add[i/2] (add is [batch,c,t/2]) */
+  const float* q; const float* z; const float* coef; const float* add;
+  float* out;
+} VqvsAffine3;
+int vqvs_affine3(const VqvsAffine3* d, void* stream);
+/* Input gradient of Conv1d(1 -> c, k = 3, pad 1) (models/classifier.py:79): dx[n,t] = sum_{c,k} w[c,0,k]*dh[n,c,t+1-k]. */
+typedef struct VqvsConvInBwd { int32_t batch, c, t, pad_; const float* dh; const float* w; float* dx; } VqvsConvInBwd;
+int vqvs_conv_in_bwd(const VqvsConvInBwd* d, void* stream);
+/*
+ * AttentionPool1d (models/classifier.py:133-191) on tokens [0 ; gelu(GN(h))]: 1x1 qkv projection, per-head softmax
+ * attention of QUERY ROW 0 only (the only row the reference keeps, :158), 1x1 output projection.  Token 0 is the zero pad,
+ * so the query is the projection's bias.  `prep` is the vqvs_gn_bwd_prep block of the GroupNorm in front (S, H are used).
+ * ws: vqvs_attnpool_workspace_bytes(batch, c, t, heads) bytes, written by fwd and read by bwd.
+ * bwd writes d_act[batch,c,t] = gradient w.r.t. gelu(GN(h)), to be fed to vqvs_gelu_bwd as d_in.
+ */
+typedef struct VqvsAttnPool {
+  int32_t batch, c, t, heads, c_out, pad_;
+  const float* h; const float* prep;
+  const float* w_qkv; const float* b_qkv;    /* [3c, c], [3c] */
+  const float* w_proj; const float* b_proj;  /* [c_out, c], [c_out] */
+  float* ws;
+  float* out;             /* fwd: [batch, c_out] */
+  const float* d_out;     /* bwd: [batch, c_out] */
+  float* d_act;           /* bwd: [batch, c, t] */
+} VqvsAttnPool;
+int64_t vqvs_attnpool_workspace_bytes(int batch, int c, int t, int heads);
+int vqvs_attnpool_fwd(const VqvsAttnPool* d, void* stream);
+int vqvs_attnpool_bwd(const VqvsAttnPool* d, void* stream);
+/* Classifier head (models/classifier.py:28-45): logits = W*gelu(stem) + b;  d_stem = gelu'(stem) * W^T d_logits. */
+typedef struct VqvsClsHead {
+  int32_t batch, dim, labels, pad_;
+  const float* stem; const float* w; const float* b;
+  float* logits; const float* d_logits; float* d_stem;
+} VqvsClsHead;
+int vqvs_cls_head_fwd(const VqvsClsHead* d, void* stream);
+int vqvs_cls_head_bwd(const VqvsClsHead* d, void* stream);
+
 /*
  * Standard-normal noise keyed by (seed, GLOBAL sample index, step) for batch-sharded sampling: out[r, :]
  * (rows of `length` floats) depends only on (seed, first_row + r, step) -- Philox4x32-10 + Box-Muller on the device.
@@ -280,6 +345,15 @@ int vqvs_vq_embed(const int64_t* idx, const float* dict, int n, int c, int t1, i
 #define VQVS_OP_FILM 7
 #define VQVS_OP_MEMSET 8
 #define VQVS_OP_DDPM_FINISH 9
+#define VQVS_OP_GN_BWD_PREP 10
+#define VQVS_OP_GELU_BWD 11
+#define VQVS_OP_GN_BWD_FINALIZE 12
+#define VQVS_OP_AFFINE3 13
+#define VQVS_OP_CONV_IN_BWD 14
+#define VQVS_OP_ATTNPOOL_FWD 15
+#define VQVS_OP_ATTNPOOL_BWD 16
+#define VQVS_OP_CLS_HEAD_FWD 17
+#define VQVS_OP_CLS_HEAD_BWD 18
 
 typedef struct VqvsFilm {
   const float* gelu_emb; const float* w_cat; const float* b_cat;
@@ -297,10 +371,10 @@ int vqvs_run(const VqvsOp* ops, int n_ops, void* stream);
  * in milliseconds (synchronises the stream at the end; measurement aid for bench.py). */
 int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 
-/* Ops executed by vqvs_run / vqvs_run_timed since the library was loaded, indexed by VQVS_OP_* (out16[VQVS_OP_CONV_UMMA] =
+/* Ops executed by vqvs_run / vqvs_run_timed since the library was loaded, indexed by VQVS_OP_* (32 slots; out32[VQVS_OP_CONV_UMMA] =
  * tcgen05 conv launches, ...; memsets are counted under VQVS_OP_MEMSET).  Evidence hook for the script-level tests and
  * bench.py's gpu_launches: a run that went through a fallback would leave these at zero. */
-int vqvs_launch_counts(unsigned long long* out16);
+int vqvs_launch_counts(unsigned long long* out32);
 
 /* Role profiler of the last vqvs_conv1d_umma launched with debug flag 512 (cycles per phase of CTA 0):
  * [0..3] transform warp 0: wait operand slot, wait raw, work, loop; [4..7] TMA; [8..11] MMA; [12..15] epilogue. */

@@ -187,9 +187,13 @@ def test_reference_namespace_shim():
 
 
 def test_classifier_matches_reference_on_cpu(golden):
-    """The guidance classifier is evaluated by ATen under autograd (any device): logits and the guidance
-    gradient of reference sample_diffusion.py:34-42 against the live reference's outputs."""
+    """Parameter layout / semantics of the guidance classifier through its ATen diagnostic (`forward_aten`, any device):
+    logits and the guidance gradient of reference sample_diffusion.py:34-42 against the live reference's outputs.  The
+    product path (`Classifier.forward`) is the native program and refuses CPU tensors (checked below)."""
+    import pytest
     import torch.nn.functional as F
+
+    from vq_voice_swap_b200.classifier import forward_aten
 
     from helpers import model_sd, rel_l2
     from vq_voice_swap_b200 import synth
@@ -200,10 +204,14 @@ def test_classifier_matches_reference_on_cpu(golden):
     x = synth.normal("clf16/x", (2, 1, 1024))
     ts = torch.tensor([0.8, 0.25])
     labels = torch.tensor([3, 6])
-    assert rel_l2(clf(x, ts).detach(), g["logits"]) <= 1e-5
-    assert rel_l2(clf(x, ts, use_checkpoint=True).detach(), g["logits"]) <= 1e-5
+    assert rel_l2(forward_aten(clf, x, ts).detach(), g["logits"]) <= 1e-5
+    assert rel_l2(forward_aten(clf, x, ts, use_checkpoint=True).detach(), g["logits"]) <= 1e-5
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        clf(x, ts)
+    with pytest.raises(RuntimeError, match="ATen diagnostic"):
+        clf.stem(x, ts)
     xg = x.clone().requires_grad_()
-    logp = F.log_softmax(clf(xg, ts), dim=-1)
+    logp = F.log_softmax(forward_aten(clf, xg, ts), dim=-1)
     grad = torch.autograd.grad(logp[range(2), labels].sum(), xg)[0] * 2.5
     assert rel_l2(grad, g["grad"]) <= 1e-4
 

@@ -5,16 +5,16 @@ state-dict names (`stem.blocks.{i}.pre_cond.2.weight`, `stem.out.1.qkv_proj.weig
 created in the reference's order, so a torch seed initialises both identically and reference
 checkpoints load.
 
-Why this module evaluates with torch ops: the only caller on the sampling path is `cond_fn`
-(reference sample_diffusion.py:34-42), which needs d log p(label | x_t, t) / d x_t through
-`torch.autograd.grad`.  The sm_100a conv programs are forward-only, so the guidance model is
-evaluated by ATen under autograd on the same device as x (first
-option); hand-written backward kernels are the section-8f "next" row.  The UNet itself, the x_{t-1}
-update and the guidance shift (`vqvs_ddpm_finish`) stay on the fused CUDA path.
-
-`EncoderPredictor` (reference models/encoder_predictor.py) is off by default in sample_vqvae.py
-and out of scope; it imports but says so when constructed.
+The only caller on the sampling path is `cond_fn` (reference sample_diffusion.py:34-42), which needs
+d log p(label | x_t, t) / d x_t through `torch.autograd.grad`.  `Classifier.forward` is a
+torch.autograd.Function (guidance.ClassifierFunction) whose forward AND backward are libvqvs launch
+programs: the stem's convolutions -- forward and transposed -- on the tcgen05 kernel, GroupNorm/GELU/
+FiLM backward, attention pool and head in hand-written CUDA (csrc/guidance.cu).  No ATen kernel runs in
+either direction.  `forward_aten` below restates the module with torch ops; it is a diagnostic (parameter
+layout cross-check on any device, A/B timing with VQVS_GUIDANCE=aten) that no product path selects.
 """
+
+import os
 
 import math
 from typing import Any, Dict, Optional, Sequence
@@ -23,8 +23,16 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import engine
 from .base import Savable
-from .unet import DEFAULT_MULT, ResBlock, TimeEmbedding, _Slot, _scaled_, group_count
+from .unet import DEFAULT_MULT, ResBlock, TimeEmbedding, UNetPredictor, _Slot, _scaled_, group_count
+
+GUIDANCE_ENGINE = "libvqvs forward + dgrad programs (guidance.ClassifierFunction)"
+
+
+def _use_aten() -> bool:
+    """VQVS_GUIDANCE=aten: evaluate the guidance model with ATen under autograd (A/B measurement only)."""
+    return os.environ.get("VQVS_GUIDANCE", "native") == "aten"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -149,6 +157,11 @@ class ClassifierStem(nn.Module):
         return time_embedding_autograd(self.time_embed, self.time_embed_extra, ts)
 
     def forward(self, x: torch.Tensor, ts: torch.Tensor, use_checkpoint: bool = False, **kwargs) -> torch.Tensor:
+        """The stem on its own is only reached through `forward_aten` (diagnostic); `Classifier.forward` runs stem and
+        head as one native program."""
+        if not _use_aten() and not getattr(self, "_aten_ok", False):
+            raise RuntimeError("ClassifierStem is evaluated inside Classifier.forward's libvqvs program; calling the stem "
+                               "alone is only available as the ATen diagnostic (classifier.forward_aten / VQVS_GUIDANCE=aten)")
         emb = self.conditional_embedding(ts, **kwargs)
         h = _conv(x, self.in_conv)
         for blk in self.blocks:
@@ -183,11 +196,17 @@ class Classifier(Savable):
         self.num_labels = num_labels
         self.stem = ClassifierStem(**kwargs)
         self.out = nn.Sequential(_Slot("gelu"), _scaled_(nn.Linear(self.stem.out_channels, num_labels), 0.0))
+        self._plans = engine.PlanCache()
 
     def forward(self, x: torch.Tensor, ts: torch.Tensor, use_checkpoint: bool = False, **kwargs) -> torch.Tensor:
-        h = self.stem(x, ts, use_checkpoint=use_checkpoint, **kwargs)
-        head = self.out[1]
-        return F.linear(F.gelu(h), head.weight, head.bias)
+        """[N x 1 x T], [N] -> logits [N x num_labels]; differentiable w.r.t. x (native dgrad program).
+        use_checkpoint trades memory for recompute in the reference; the native program keeps what it needs."""
+        if _use_aten():
+            return forward_aten(self, x, ts, use_checkpoint=use_checkpoint)
+        from .guidance import ClassifierFunction
+
+        engine._require_cuda(x, ts)
+        return ClassifierFunction.apply(x, ts, self)
 
     def save_kwargs(self) -> Dict[str, Any]:
         return dict(
@@ -197,6 +216,18 @@ class Classifier(Savable):
             output_mult=self.stem.output_mult,
             depth_mult=self.stem.depth_mult,
         )
+
+
+def forward_aten(clf: "Classifier", x: torch.Tensor, ts: torch.Tensor, use_checkpoint: bool = False) -> torch.Tensor:
+    """Diagnostic: the same parameters evaluated with torch ops under autograd (any device).  Not a fallback -- nothing in
+    the package calls it unless VQVS_GUIDANCE=aten is set for an A/B timing."""
+    clf.stem._aten_ok = True
+    try:
+        h = clf.stem(x, ts, use_checkpoint=use_checkpoint)
+    finally:
+        clf.stem._aten_ok = False
+    head = clf.out[1]
+    return F.linear(F.gelu(h), head.weight, head.bias)
 
 
 class EncoderPredictor(Savable):

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
 int run_film(const VqvsFilm* f, void* stream);
 
 // kernels launched through vqvs_run / vqvs_run_timed since the library was loaded, per op kind (vqvs_launch_counts)
-static unsigned long long g_launches[16];
+static unsigned long long g_launches[32];
 
 }  // namespace vqvs
 
@@ -84,6 +84,15 @@ static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev)
       case VQVS_OP_TIME_EMBED: rc = vqvs_time_embed((const VqvsTimeEmbed*)p, stream); break;
       case VQVS_OP_FILM: rc = vqvs::run_film((const VqvsFilm*)p, stream); break;
       case VQVS_OP_DDPM_FINISH: rc = vqvs_ddpm_finish((const VqvsDdpmFinish*)p, stream); break;
+      case VQVS_OP_GN_BWD_PREP: rc = vqvs_gn_bwd_prep(((const VqvsGnBwdPrep*)p)->gn, ((const VqvsGnBwdPrep*)p)->prep, stream); break;
+      case VQVS_OP_GELU_BWD: rc = vqvs_gelu_bwd((const VqvsGeluBwd*)p, stream); break;
+      case VQVS_OP_GN_BWD_FINALIZE: rc = vqvs_gn_bwd_finalize((const VqvsGnBwdFinalize*)p, stream); break;
+      case VQVS_OP_AFFINE3: rc = vqvs_affine3((const VqvsAffine3*)p, stream); break;
+      case VQVS_OP_CONV_IN_BWD: rc = vqvs_conv_in_bwd((const VqvsConvInBwd*)p, stream); break;
+      case VQVS_OP_ATTNPOOL_FWD: rc = vqvs_attnpool_fwd((const VqvsAttnPool*)p, stream); break;
+      case VQVS_OP_ATTNPOOL_BWD: rc = vqvs_attnpool_bwd((const VqvsAttnPool*)p, stream); break;
+      case VQVS_OP_CLS_HEAD_FWD: rc = vqvs_cls_head_fwd((const VqvsClsHead*)p, stream); break;
+      case VQVS_OP_CLS_HEAD_BWD: rc = vqvs_cls_head_bwd((const VqvsClsHead*)p, stream); break;
       case VQVS_OP_MEMSET: {
         const VqvsMemset* m = (const VqvsMemset*)p;
         cudaError_t e = cudaMemsetAsync(m->ptr, 0, (size_t)m->bytes, (cudaStream_t)stream);
@@ -104,17 +113,17 @@ static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev)
       vqvs::set_error("vqvs_run: op %d (kind %d) failed: %s", i, ops[i].kind, msg);
       return rc;
     }
-    if (ops[i].kind > 0 && ops[i].kind < 16) __atomic_fetch_add(&vqvs::g_launches[ops[i].kind], 1ull, __ATOMIC_RELAXED);
+    if (ops[i].kind > 0 && ops[i].kind < 32) __atomic_fetch_add(&vqvs::g_launches[ops[i].kind], 1ull, __ATOMIC_RELAXED);
     if (ev) cudaEventRecord(ev[i + 1], (cudaStream_t)stream);
   }
   return VQVS_OK;
 }
 
-extern "C" int vqvs_launch_counts(unsigned long long* out16) {
+extern "C" int vqvs_launch_counts(unsigned long long* out16) {  // 32 slots
   if (!out16) {
     vqvs::set_error("vqvs_launch_counts: null pointer");
     return VQVS_EINVAL;
   }
-  for (int i = 0; i < 16; ++i) out16[i] = __atomic_load_n(&vqvs::g_launches[i], __ATOMIC_RELAXED);
+  for (int i = 0; i < 32; ++i) out16[i] = __atomic_load_n(&vqvs::g_launches[i], __ATOMIC_RELAXED);
   return VQVS_OK;
 }

@@ -224,22 +224,27 @@ def conv_precision(c_out: int, base_channels: Optional[int]) -> int:
     return L.PREC_BF16X3
 
 
-def _pack(conv: torch.nn.Conv1d, skip: Optional[torch.nn.Conv1d], prec: int = L.PREC_BF16X3) -> Optional[Packed]:
+def pack_weights(weight: torch.Tensor, skip_weight: Optional[torch.Tensor], prec: int = L.PREC_BF16X3) -> Optional[Packed]:
+    """fp32 [c_out, c_in, k] (+ optional 1x1 skip [c_out, c_skip, 1]) -> tcgen05 operand image, or None if unsupported."""
     lib = L.load()
-    c_out, c_in, k = conv.weight.shape
-    c_skip = skip.weight.shape[1] if skip is not None else 0
+    c_out, c_in, k = weight.shape
+    c_skip = skip_weight.shape[1] if skip_weight is not None else 0
     nbytes = lib.vqvs_packed_weight_bytes(c_out, c_in, k, c_skip, prec)
     if nbytes <= 0:
         return None
-    img = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
-    w = _f32(conv.weight)
-    ws = _f32(skip.weight) if skip is not None else None
-    dev = conv.weight.device
+    dev = weight.device
+    img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    w = _f32(weight)
+    ws = _f32(skip_weight) if skip_weight is not None else None
     with torch.cuda.device(dev):
         L.check(lib.vqvs_pack_conv_weights(L.ptr(w), L.ptr(ws), c_out, c_in, k, c_skip, prec, L.ptr(img), L.stream_ptr(dev)),
                 "vqvs_pack_conv_weights")
         torch.cuda.current_stream(dev).synchronize()  # w / ws temporaries may be freed after this
     return Packed(img, prec)
+
+
+def _pack(conv: torch.nn.Conv1d, skip: Optional[torch.nn.Conv1d], prec: int = L.PREC_BF16X3) -> Optional[Packed]:
+    return pack_weights(conv.weight, skip.weight if skip is not None else None, prec)
 
 
 def _skip_proj(block):
@@ -276,7 +281,7 @@ def weights_for(net, blocks: Sequence, backend: str, reduced_precision: bool = F
                 if isinstance(conv, torch.nn.Conv1d):
                     w.packed[(id(net), name)] = _pack(conv, None)
             head = getattr(net, "out", None)
-            if head is not None and head[1].weight.shape[0] > 1:
+            if head is not None and isinstance(head[1], torch.nn.Conv1d) and head[1].weight.shape[0] > 1:
                 w.packed[(id(net), "out")] = _pack(head[1], None)
         film = [b for b in blocks if getattr(b, "emb_channels", None)]
         if film:

@@ -10,12 +10,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 RESIZE_NONE, RESIZE_DOWN2, RESIZE_UP2 = 0, 1, 2
 SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
 OP_CONV_SIMT, OP_CONV_UMMA, OP_GN_FINALIZE, OP_CONV_IN, OP_CONV_OUT = 1, 2, 3, 4, 5
 OP_TIME_EMBED, OP_FILM, OP_MEMSET, OP_DDPM_FINISH = 6, 7, 8, 9
+OP_GN_BWD_PREP, OP_GELU_BWD, OP_GN_BWD_FINALIZE, OP_AFFINE3, OP_CONV_IN_BWD = 10, 11, 12, 13, 14
+OP_ATTNPOOL_FWD, OP_ATTNPOOL_BWD, OP_CLS_HEAD_FWD, OP_CLS_HEAD_BWD = 15, 16, 17, 18
 CONV_PAIR_STATS = 1024  # VqvsConv.reserved_ flag
 CONV_STAT_GRAN_SHIFT = 12  # bits 12..15 of VqvsConv.reserved_: log2 of the statistics granularity
 CONV_PREC_SHIFT = 16  # bits 16..17 of VqvsConv.reserved_: tensor-core operand format
@@ -79,6 +81,40 @@ class Film(C.Structure):
     ]
 
 
+class GnBwdPrep(C.Structure):
+    _fields_ = [("gn", _p), ("prep", _p)]
+
+
+class GeluBwd(C.Structure):
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("up", _i32),
+                ("d_in", _p), ("z", _p), ("prep", _p), ("q", _p), ("acc", _p)]
+
+
+class GnBwdFinalize(C.Structure):
+    _fields_ = [("batch", _i32), ("c", _i32), ("groups", _i32), ("pad_", _i32), ("count", _i64),
+                ("acc", _p), ("prep", _p), ("coef", _p)]
+
+
+class Affine3(C.Structure):
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("add_mode", _i32),
+                ("q", _p), ("z", _p), ("coef", _p), ("add", _p), ("out", _p)]
+
+
+class ConvInBwd(C.Structure):
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("pad_", _i32), ("dh", _p), ("w", _p), ("dx", _p)]
+
+
+class AttnPool(C.Structure):
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("heads", _i32), ("c_out", _i32), ("pad_", _i32),
+                ("h", _p), ("prep", _p), ("w_qkv", _p), ("b_qkv", _p), ("w_proj", _p), ("b_proj", _p),
+                ("ws", _p), ("out", _p), ("d_out", _p), ("d_act", _p)]
+
+
+class ClsHead(C.Structure):
+    _fields_ = [("batch", _i32), ("dim", _i32), ("labels", _i32), ("pad_", _i32),
+                ("stem", _p), ("w", _p), ("b", _p), ("logits", _p), ("d_logits", _p), ("d_stem", _p)]
+
+
 class Memset(C.Structure):
     _fields_ = [("ptr", _p), ("bytes", _i64)]
 
@@ -108,6 +144,16 @@ SIGNATURES = {
     "vqvs_film_linear": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_vq_argmin": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "vqvs_vq_embed": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "vqvs_gn_bwd_prep": (C.c_int, [C.POINTER(GnFinalize), _p, _p]),
+    "vqvs_gelu_bwd": (C.c_int, [C.POINTER(GeluBwd), _p]),
+    "vqvs_gn_bwd_finalize": (C.c_int, [C.POINTER(GnBwdFinalize), _p]),
+    "vqvs_affine3": (C.c_int, [C.POINTER(Affine3), _p]),
+    "vqvs_conv_in_bwd": (C.c_int, [C.POINTER(ConvInBwd), _p]),
+    "vqvs_attnpool_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vqvs_attnpool_fwd": (C.c_int, [C.POINTER(AttnPool), _p]),
+    "vqvs_attnpool_bwd": (C.c_int, [C.POINTER(AttnPool), _p]),
+    "vqvs_cls_head_fwd": (C.c_int, [C.POINTER(ClsHead), _p]),
+    "vqvs_cls_head_bwd": (C.c_int, [C.POINTER(ClsHead), _p]),
     "vqvs_keyed_normal": (C.c_int, [_p, C.c_int, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, _p]),
     "vqvs_run": (C.c_int, [C.POINTER(Op), C.c_int, _p]),
     "vqvs_run_timed": (C.c_int, [C.POINTER(Op), C.c_int, _p, C.POINTER(C.c_float)]),
@@ -150,12 +196,15 @@ def check(rc: int, what: str = "libvqvs") -> None:
 
 OP_NAMES = {OP_CONV_SIMT: "conv_simt", OP_CONV_UMMA: "conv_umma", OP_GN_FINALIZE: "gn_finalize", OP_CONV_IN: "conv_in",
             OP_CONV_OUT: "conv_out", OP_TIME_EMBED: "time_embed", OP_FILM: "film", OP_MEMSET: "memset",
-            OP_DDPM_FINISH: "ddpm_finish"}
+            OP_DDPM_FINISH: "ddpm_finish", OP_GN_BWD_PREP: "gn_bwd_prep", OP_GELU_BWD: "gelu_bwd",
+            OP_GN_BWD_FINALIZE: "gn_bwd_finalize", OP_AFFINE3: "affine3", OP_CONV_IN_BWD: "conv_in_bwd",
+            OP_ATTNPOOL_FWD: "attnpool_fwd", OP_ATTNPOOL_BWD: "attnpool_bwd", OP_CLS_HEAD_FWD: "cls_head_fwd",
+            OP_CLS_HEAD_BWD: "cls_head_bwd"}
 
 
 def launch_counts() -> dict:
     """Ops executed through vqvs_run since the library was loaded, by name (include/vqvs.h: vqvs_launch_counts)."""
-    buf = (C.c_uint64 * 16)()
+    buf = (C.c_uint64 * 32)()
     check(load().vqvs_launch_counts(buf), "vqvs_launch_counts")
     return {name: int(buf[kind]) for kind, name in OP_NAMES.items()}
 
