@@ -386,7 +386,7 @@ def guidance_share(model, clf, x, labels):
     from vq_voice_swap_b200 import classifier as C
 
     return {"predictor_ms": round(t_pred, 2), "cond_fn_ms": round(t_guid, 2), "cond_fn_share": round(t_guid / (t_pred + t_guid), 3),
-            "cond_fn_engine": getattr(C, "GUIDANCE_ENGINE", "ATen/cuDNN under autograd")}
+            "cond_fn_engine": "ATen/cuDNN under autograd (VQVS_GUIDANCE=aten)" if C._use_aten() else C.GUIDANCE_ENGINE}
 
 
 # ---------------------------------------------------------------------------------------------
