@@ -166,6 +166,18 @@ def vqvae_small():
     save("vqvae_bc16.npz", codes=codes.numpy(), encoder_out=enc_out.numpy(), audio=audio.numpy())
 
 
+def vqvae_uncond():
+    """decode_uncond_guidance (vq_vae.py:147-220).  The reference always repeats x three times (:191-193), so it only works
+    with BOTH guidance scales non-zero; label 0 is the unconditional label, real labels are offset by one."""
+    m = VQVAE(base_channels=16, num_labels=4, cond_mult=3, dictionary_size=64, pred_name="unet").eval()
+    synth.load_synth(m, tag="vqvae16u")
+    codes = synth.integers("vqvae16u/codes", (2, 2), 64)
+    labels = torch.tensor([2, 0])
+    with _Inject("vqvae16u/decode"):
+        audio = m.decode_uncond_guidance(codes, labels, steps=3, constrain=True, label_scale=1.3, vq_scale=0.7)
+    save("vqvae_uncond_bc16.npz", audio=audio.numpy())
+
+
 def classifier_small():
     """Classifier logits, the guidance gradient of sample_diffusion.py:34-42, and one guided ddpm_previous."""
     import torch.nn.functional as F
@@ -222,10 +234,14 @@ if __name__ == "__main__":
         classifier_small()
         keys()
         sys.exit(0)
+    if sys.argv[1:] == ["uncond"]:
+        vqvae_uncond()
+        sys.exit(0)
     resblocks()
     unet_small()
     vq_cases()
     ddpm()
     vqvae_small()
+    vqvae_uncond()
     classifier_small()
     keys()

@@ -307,6 +307,70 @@ def test_vqvae_encode_decode_golden(golden, monkeypatch, backend):
     assert rel_l2(audio.cpu(), g["audio"]) <= 1e-3
 
 
+def test_decode_uncond_guidance_golden(golden, monkeypatch):
+    """Classifier-free-guided decode (reference vq_vae.py:147-220) against the live reference: three predictor batches per
+    step (conditional, codes dropped, label dropped) mixed linearly.  The reference repeats x three times unconditionally
+    (:191-193), so both guidance scales are non-zero; label 0 is the unconditional label."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    from vq_voice_swap_b200.vq_vae import VQVAE
+
+    m = VQVAE(base_channels=16, num_labels=4, cond_mult=3, dictionary_size=64, pred_name="unet")
+    m.load_state_dict(synth.synth_state_dict(synth.shapes_of(m), tag="vqvae16u"))
+    m = m.to(DEV).eval()
+    codes = synth.integers("vqvae16u/codes", (2, 2), 64).to(DEV)
+    monkeypatch.setattr(torch, "randn", lambda *s, **k: synth.normal("vqvae16u/decode/x_T", s))
+    _Noise("vqvae16u/decode", monkeypatch)
+    audio = m.decode_uncond_guidance(codes, torch.tensor([2, 0], device=DEV), steps=3, constrain=True, label_scale=1.3,
+                                     vq_scale=0.7)
+    assert rel_l2(audio.cpu(), golden("vqvae_uncond_bc16.npz")["audio"]) <= 1e-3
+    # one guidance term only: a 2x batch (the reference's fixed 3x repeat cannot run this case)
+    only_vq = m.decode_uncond_guidance(codes, torch.tensor([2, 0], device=DEV), steps=2, vq_scale=0.5)
+    assert only_vq.shape == (2, 1, 512) and torch.isfinite(only_vq).all()
+
+
+def test_config3_full_size_codes_and_audio_vs_oracle(monkeypatch):
+    """BASELINE configs[2] at size: VQVAE bc32 (encoder -> 512-way arg-min over 512-channel vectors at T1 = 250 ->
+    conditional constrained decode) on 64000-sample waveforms.  Code indices must equal the oracle's wherever the
+    oracle's top-2 distance gap ON THE ENCODER'S OWN OUTPUTS exceeds the margin the encoder's error can move a distance by
+    (SURVEY.md 8c); audio of a 4-step injected-noise decode within 1e-3."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    from vq_voice_swap_b200.vq_vae import VQVAE
+
+    m = VQVAE(base_channels=32, pred_name="unet", enc_name="unet", cond_mult=16, dictionary_size=512, num_labels=8)
+    sd = synth.synth_state_dict(synth.shapes_of(m), tag="cfg3")
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    batch = 3
+    w = synth.normal("cfg3/wave", (batch, 1, 64000)).clamp(-1, 1)
+    enc_ref = O.unet_encoder(sd, w)
+    enc = m.encoder(w.to(DEV)).cpu()
+    enc_err = rel_l2(enc, enc_ref)
+    assert enc_err <= 1e-4  # the encoder keeps bf16x3 everywhere (its outputs decide code indices)
+    ref_codes = O.vq_encode(sd["vq.dictionary"], enc_ref)
+    codes = m.encode(w.to(DEV)).cpu()
+    assert codes.shape == (batch, 250) and codes.dtype == torch.int64
+    gap, mag = O.vq_top2_gap(sd["vq.dictionary"], enc_ref)
+    # a perturbation dx of the encoder output moves a distance by <= 2*|dx|*(|x| + |d|): bound it with the measured error
+    xn = enc_ref.permute(0, 2, 1).reshape(-1, enc_ref.shape[1]).norm(dim=-1).reshape(batch, -1)
+    dn = sd["vq.dictionary"].norm(dim=-1).max()
+    per_vec = (enc - enc_ref).permute(0, 2, 1).reshape(-1, enc_ref.shape[1]).norm(dim=-1).reshape(batch, -1)
+    margin = 4 * per_vec * (xn + dn) + 64 * np.finfo(np.float32).eps * mag
+    decisive = gap > margin
+    assert torch.equal(codes[decisive], ref_codes[decisive])
+    assert int((codes != ref_codes).sum()) <= int((~decisive).sum())
+    assert float(decisive.float().mean()) >= 0.97, "the margin must leave almost every vector decisive"
+    # 4-step constrained decode from the ORACLE's codes with injected noise
+    labels = torch.tensor([1, 5, 2])
+    steps = 4
+    x_T = synth.normal("cfg3/decode/x_T", (batch, 1, 64000))
+    noises = [synth.normal(f"cfg3/decode/noise{i}", x_T.shape) for i in range(steps)]
+    ref_audio = O.vqvae_decode(sd, "exp", ref_codes, labels, steps, x_T, noises, constrain=True)
+    monkeypatch.setattr(torch, "randn", lambda *s, **k: x_T.clone())
+    _Noise("cfg3/decode", monkeypatch)
+    audio = m.decode(ref_codes.to(DEV), labels.to(DEV), steps=steps, constrain=True)
+    assert rel_l2(audio.cpu(), ref_audio) <= 1e-3
+
+
 def test_fused_sampler_matches_unfused(monkeypatch, backend):
     """ddpm_sample with the update fused into the UNet's last kernel == predictor() + ddpm_previous()."""
     m = _diffusion_model("diffusion_unet16", "unet16")

@@ -226,3 +226,43 @@ def test_classifier_zero_head_and_checkpoint_roundtrip(tmp_path):
     assert again.save_kwargs() == clf.save_kwargs() and again.num_labels == 5
     pred = _dm("unet", 16).predictor
     assert clf.stem.load_from_predictor(pred) > 0  # reference models/classifier.py:123-130
+
+
+def test_audio_io_wav_roundtrip_uses_the_reference_sample_convention(tmp_path):
+    """ffmpeg-free ChunkWriter / ChunkReader (reference dataset.py:167-303 pipes s16le through ffmpeg): a float chunk is
+    clipped, scaled by 2**15 - 1 and truncated toward zero on write (:296-299) and divided by 2**15 on read (:225)."""
+    import numpy as np
+    import wave
+
+    from vq_voice_swap_b200.audio_io import ChunkReader, ChunkWriter, decode_u_law, encode_u_law
+
+    x = np.concatenate([np.linspace(-1.2, 1.2, 4001), [0.0, 1e-5, -1e-5, 0.5, -0.5]]).astype(np.float32)
+    path = str(tmp_path / "a.wav")
+    wr = ChunkWriter(path, 16000)
+    wr.write(x[:1000])
+    wr.write(x[1000:])
+    wr.close()
+    with wave.open(path, "rb") as f:
+        assert (f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()) == (16000, 1, 2, len(x))
+        pcm = np.frombuffer(f.readframes(len(x)), dtype="<i2")
+    assert np.array_equal(pcm, (np.clip(x, -1, 1) * (2 ** 15 - 1)).astype("int16"))  # the reference's exact expression
+    rd = ChunkReader(path, 16000)
+    a, b, c = rd.read(1500), rd.read(10 ** 6), rd.read(10)
+    rd.close()
+    assert c is None and len(a) == 1500 and len(a) + len(b) == len(x)
+    assert np.array_equal(np.concatenate([a, b]), pcm.astype("float32") / 2 ** 15)
+    # u-law: written decoded to linear, read re-encoded (reference encode_from_linear / decode_to_linear)
+    u = np.linspace(-1, 1, 513).astype(np.float32)
+    assert np.allclose(encode_u_law(decode_u_law(u)), u, atol=1e-6)
+    path_u = str(tmp_path / "u.wav")
+    wr = ChunkWriter(path_u, 16000, encoding="ulaw")
+    wr.write(u)
+    wr.close()
+    rd = ChunkReader(path_u, 16000, encoding="ulaw")
+    back = rd.read(len(u))
+    rd.close()
+    assert np.abs(back - u).max() < 0.02  # 16-bit linear quantisation seen through the u-law curve near zero
+    import pytest
+
+    with pytest.raises(ValueError):
+        ChunkReader(str(tmp_path / "a.mp3"), 16000)

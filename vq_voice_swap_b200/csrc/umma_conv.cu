@@ -891,6 +891,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const int total_stages = g.main_stages + g.skip_stages;
+  // Programmatic dependent launch (the 130 convs of a UNet step form one chain on one stream): the next conv may be
+  // scheduled as soon as every CTA of this grid got here, so its CTAs take over SMs as ours retire and run their own
+  // prologue (mbarrier init, TMEM allocation, resident weight load) under our tail; everything that reads what the
+  // PREVIOUS grid wrote (activations, statistics, skip inputs) waits for that grid to complete.  Both instructions are
+  // no-ops for a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (warp != TMA_W_WARP) asm volatile("griddepcontrol.wait;" ::: "memory");
 
 // Register budget: 640 threads x 96 registers (the launch bound) for every role.  Per-role budgets via setmaxnreg
 // were tried (72/128, 56/96/112): the halo transform warp then runs spilling code on the critical path of every
@@ -1698,11 +1705,20 @@ static cudaError_t launch_kind_impl(VQVS_LAUNCHER_ARGS) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = !getenv("VQVS_NO_PDL");
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (mt == 2 && KIND != 3)
-    conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND><<<grid, THREADS, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
-  else
-    conv_umma_kernel<1, KIND><<<grid, THREADS, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
-  return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND>, maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, KIND>, maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
 }
 #if VQVS_KIND_TU == 0
 cudaError_t launch_kind0(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<0>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
@@ -1961,8 +1977,50 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps, keyed by (base pointer, rows, length, box width): a plan launches the same convs over the same
+// buffers every diffusion step, and cuTensorMapEncodeTiled costs ~1 us each -- up to four per conv, 130 convs per step,
+// which is what bounds small batches.  (The only global mutable state of the library besides the error string.)
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct MapKey {
+  const void* base;
+  int rows, t, box_w;
+  bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && t == o.t && box_w == o.box_w; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= (size_t)k.t * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    return h ^ ((size_t)k.box_w << 48);
+  }
+};
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+}  // namespace
+
+static int encode_map_uncached(CUtensorMap* m, const float* base, int rows, int t, int box_w);
 // [rows = batch*channels][t] fp32 tensor, boxes of 16 rows x box_w positions, zero fill outside.
 static int encode_map(CUtensorMap* m, const float* base, int rows, int t, int box_w) {
+  const MapKey key{base, rows, t, box_w};
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *m = it->second;
+      return VQVS_OK;
+    }
+  }
+  const int rc = encode_map_uncached(m, base, rows, t, box_w);
+  if (rc == VQVS_OK) {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();  // (a descriptor only encodes address + geometry: stale entries are harmless)
+    g_map_cache.emplace(key, *m);
+  }
+  return rc;
+}
+static int encode_map_uncached(CUtensorMap* m, const float* base, int rows, int t, int box_w) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("conv(umma): cuTensorMapEncodeTiled is not available from the driver");
