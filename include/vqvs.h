@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 4
+#define VQVS_ABI_VERSION 5
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -287,6 +287,27 @@ typedef struct VqvsClsHead {
 } VqvsClsHead;
 int vqvs_cls_head_fwd(const VqvsClsHead* d, void* stream);
 int vqvs_cls_head_bwd(const VqvsClsHead* d, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* ConvMFCCEncoder front end (reference models/conv_encoder.py:14-147, version 1 -- the encoder of the published
+ * vqvae-unet-mfcc checkpoint): inverse mu-law (:146-147) -> torchaudio MFCC (n_fft = 2*hop Hann frames, centre/reflect,
+ * power spectrum, mel filter bank, log(mel + 1e-6), DCT) -> deltas and delta-deltas (:136-143).
+ * window [n_fft], cos_t / sin_t [n_bins, n_fft] (DFT basis), fb [n_bins, n_mels], dct [n_mels, n_mfcc]: device copies of
+ * the module's buffers.  mfcc: scratch [batch, n_mfcc, frames]; out: [batch, c_pad, frames], channels >= 3*n_mfcc zeroed
+ * (c_pad rounds 39 up to the conv kernel's 16-channel granularity). */
+typedef struct VqvsMfcc {
+  int32_t batch, t, n_fft, hop, n_bins, n_mels, n_mfcc, frames, c_pad, ulaw;
+  const float* x; const float* window; const float* cos_t; const float* sin_t; const float* fb; const float* dct;
+  float* mfcc; float* out;
+} VqvsMfcc;
+int vqvs_mfcc39(const VqvsMfcc* d, void* stream);
+/* out[row, i] = (res ? res[row, i] : 0) + GELU(h[row, i]), i < t: the "conv -> GELU (-> + x)" blocks of
+ * conv_encoder.py:63-86,121-133 (rows = batch*channels; pitches in floats). */
+int vqvs_gelu_add(const float* h, int h_pitch, const float* res, int res_pitch, float* out, int out_pitch, int rows, int t,
+                  void* stream);
+/* even[row, j] = x[row, 2j], odd[row, j] = x[row, 2j+1] (zero past the end): turns the stride-2, k = 4 conv of
+ * conv_encoder.py:68-73 into a k = 3 conv over the channel concatenation [even ; odd]. */
+int vqvs_deinterleave2(const float* x, int rows, int t, float* even, float* odd, int t_half, void* stream);
 
 /*
  * Standard-normal noise keyed by (seed, GLOBAL sample index, step) for batch-sharded sampling: out[r, :]

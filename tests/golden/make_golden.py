@@ -178,6 +178,25 @@ def vqvae_uncond():
     save("vqvae_uncond_bc16.npz", audio=audio.numpy())
 
 
+def conv_mfcc():
+    """ConvMFCCEncoder (models/conv_encoder.py) version 1, mu-law and linear input; only the conv stack's parameters are
+    re-randomised (the transform's window / filter bank / DCT buffers keep torchaudio's values)."""
+    from vq_voice_swap.models.conv_encoder import ConvMFCCEncoder
+
+    out = {}
+    for name, ulaw in (("ulaw", True), ("linear", False)):
+        m = ConvMFCCEncoder(base_channels=8, out_channels=32, input_ulaw=ulaw).eval()
+        sd = m.state_dict()
+        shapes = {k: (tuple(v.shape), v.dtype) for k, v in sd.items() if k.startswith("blocks.")}
+        sd.update(synth.synth_state_dict(shapes, tag="convmfcc"))
+        m.load_state_dict(sd)
+        x = (0.4 * synth.normal("convmfcc/x", (2, 1, 6400))).clamp(-1, 1)
+        out[name] = m(x).numpy()
+        out[name + "_mfcc"] = m.mfcc(x[:, 0] if not ulaw else x[:, 0].sign() * (1 / 255.0) * (256.0 ** x[:, 0].abs() - 1)).numpy()
+    out["keys"] = np.array([f"{k}|{tuple(v.shape)}" for k, v in m.state_dict().items()])
+    save("conv_mfcc.npz", **out)
+
+
 def classifier_small():
     """Classifier logits, the guidance gradient of sample_diffusion.py:34-42, and one guided ddpm_previous."""
     import torch.nn.functional as F
@@ -237,11 +256,15 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["uncond"]:
         vqvae_uncond()
         sys.exit(0)
+    if sys.argv[1:] == ["mfcc"]:
+        conv_mfcc()
+        sys.exit(0)
     resblocks()
     unet_small()
     vq_cases()
     ddpm()
     vqvae_small()
     vqvae_uncond()
+    conv_mfcc()
     classifier_small()
     keys()

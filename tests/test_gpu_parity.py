@@ -486,3 +486,42 @@ def test_batch_64_samples_are_independent(unet64, monkeypatch):
         # -- atomic summation order -- to whole fp16 ulps in a few elements)
         assert rel_l2(alone.cpu(), full[i:i + 1].cpu()) <= 1e-4
     assert torch.isfinite(full).all()
+
+
+# ---------------------------------------------------------------------------
+# ConvMFCCEncoder (the published checkpoint's encoder): MFCC front end + conv stack against the live reference
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,ulaw", [("ulaw", True), ("linear", False)])
+def test_conv_mfcc_encoder_golden(golden, name, ulaw):
+    from vq_voice_swap_b200.conv_encoder import ConvMFCCEncoder
+
+    g = golden("conv_mfcc.npz")
+    m = ConvMFCCEncoder(base_channels=8, out_channels=32, input_ulaw=ulaw).eval()
+    assert [f"{k}|{tuple(v.shape)}" for k, v in m.state_dict().items()] == list(g["keys"])  # reference checkpoints load
+    sd = m.state_dict()
+    shapes = {k: (tuple(v.shape), v.dtype) for k, v in sd.items() if k.startswith("blocks.")}
+    sd.update(synth.synth_state_dict(shapes, tag="convmfcc"))
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    x = (0.4 * synth.normal("convmfcc/x", (2, 1, 6400))).clamp(-1, 1).to(DEV)
+    y = m(x)
+    assert y.shape == (2, 32, 20) and m.downsample_rate == 320
+    # log-mel features amplify fp32 summation-order differences of near-silent bins; the conv stack is bf16x3
+    assert rel_l2(y.cpu(), g[name]) <= 1e-3
+
+
+def test_vqvae_with_mfcc_encoder_runs_end_to_end():
+    """VQVAE(enc_name='conv-mfcc-ulaw'): the published model's layout (encoder rate 320 vs predictor rate 256)."""
+    from vq_voice_swap_b200.vq_vae import VQVAE
+
+    m = VQVAE(base_channels=16, enc_name="conv-mfcc-ulaw", cond_mult=4, dictionary_size=32, num_labels=3, pred_name="unet")
+    sd = m.state_dict()
+    shapes = {k: (tuple(v.shape), v.dtype) for k, v in sd.items() if ".mfcc." not in k}
+    sd.update(synth.synth_state_dict(shapes, tag="vqvae_mfcc"))
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    w = (0.4 * synth.normal("vqvae_mfcc/w", (2, 1, 6400))).clamp(-1, 1).to(DEV)
+    codes = m.encode(w)
+    assert codes.shape == (2, 20) and codes.dtype == torch.int64
+    audio = m.decode(codes, torch.tensor([0, 2], device=DEV), steps=2, constrain=True)
+    assert audio.shape == (2, 1, 6400) and torch.isfinite(audio).all()

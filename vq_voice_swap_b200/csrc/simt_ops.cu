@@ -322,28 +322,46 @@ __global__ void gelu_kernel(const float* __restrict__ in, float* __restrict__ ou
     out[i] = gelu_erf(in[i]);
 }
 
+// ab[n, o] = b[o] + sum_j w[o, j] * g[n, j]: a [n_out x dim] x [dim x batch] product (26 000 x 256 x 64 for unet64) as a
+// register-tiled CUDA-core GEMM: 64 outputs x 64 samples per CTA, 4 x 4 per thread, K staged 16 at a time.  (One warp per
+// output with a shuffle reduction per sample took 0.36 ms of every UNet step.)
+constexpr int FL_TILE = 64, FL_K = 16;
 __global__ void __launch_bounds__(256) film_linear_kernel(VqvsFilm d) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + warp;
-  if (o >= d.n_out) return;
-  const float* wr = d.w_cat + (size_t)o * d.dim;
-  float w[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int j = lane + 32 * i;
-    w[i] = j < d.dim ? wr[j] : 0.f;
-  }
-  const float b = d.b_cat[o];
-  for (int n = 0; n < d.batch; ++n) {
-    const float* g = d.gelu_emb + (size_t)n * d.dim;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int j = lane + 32 * i;
-      if (j < d.dim) acc += w[i] * g[j];
+  __shared__ float ws[FL_K][FL_TILE + 1], gs[FL_K][FL_TILE + 1];
+  const int o0 = blockIdx.x * FL_TILE, n0 = blockIdx.y * FL_TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> 4 outputs, ty -> 4 samples
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < d.dim; k0 += FL_K) {
+    for (int i = threadIdx.x; i < FL_TILE * FL_K; i += 256) {
+      const int r = i / FL_K, k = i - r * FL_K;  // consecutive threads read consecutive k of one row: 64-B segments
+      ws[k][r] = (o0 + r < d.n_out && k0 + k < d.dim) ? d.w_cat[(size_t)(o0 + r) * d.dim + k0 + k] : 0.f;
+      gs[k][r] = (n0 + r < d.batch && k0 + k < d.dim) ? d.gelu_emb[(size_t)(n0 + r) * d.dim + k0 + k] : 0.f;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) d.ab[(size_t)n * d.n_out + o] = acc + b;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FL_K; ++k) {
+      float wv[4], gv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wv[i] = ws[k][tx + 16 * i];
+        gv[i] = gs[k][ty + 16 * i];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(gv[a], wv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int n = n0 + ty + 16 * a;
+    if (n >= d.batch) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int o = o0 + tx + 16 * b;
+      if (o < d.n_out) d.ab[(size_t)n * d.n_out + o] = acc[a][b] + d.b_cat[o];
+    }
   }
 }
 
@@ -762,8 +780,8 @@ extern "C" int vqvs_gelu(const float* in, float* out, int64_t n, void* stream) {
 
 static int launch_film(const VqvsFilm& f, void* stream) {
   VQVS_CHECK_ARG(f.gelu_emb && f.w_cat && f.b_cat && f.ab && f.batch > 0 && f.n_out > 0, "film_linear: bad arguments");
-  VQVS_CHECK_ARG(f.dim > 0 && f.dim <= 1024, "film_linear: dim %d outside (0,1024]", f.dim);
-  film_linear_kernel<<<ceil_div(f.n_out, 8), 256, 0, (cudaStream_t)stream>>>(f);
+  VQVS_CHECK_ARG(f.dim > 0, "film_linear: dim must be positive");
+  film_linear_kernel<<<dim3(ceil_div(f.n_out, FL_TILE), ceil_div(f.batch, FL_TILE)), 256, 0, (cudaStream_t)stream>>>(f);
   VQVS_CHECK_LAUNCH("vqvs_film_linear");
   return VQVS_OK;
 }

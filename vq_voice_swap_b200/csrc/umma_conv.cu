@@ -150,8 +150,14 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   off = align_up(off, 128);
   g->off_w = off;
   const long long w_img = g->per_tile_bytes;
-  static const int resident_kb = getenv("VQVS_RESIDENT_KB") ? atoi(getenv("VQVS_RESIDENT_KB")) : 150;  // tuning aid (147 KB: the 192 -> 64 concat convs)
+  // Resident weights leave room for 2-K-block stages only once the image passes ~90 KB (128 -> 64: 98 KB, 192 -> 64: 147 KB);
+  // streaming those through the weight ring with 4-K-block stages and one time tile per item measured 5-18 % faster
+  // (profiles/r2_*: the transform warps' per-stage overhead is what the larger stage amortises).  Wider N tiles keep the
+  // 150 KB limit (nothing between 90 and 150 KB occurs there).
+  static const int resident_kb_env = getenv("VQVS_RESIDENT_KB") ? atoi(getenv("VQVS_RESIDENT_KB")) : 0;  // tuning aid
+  const int resident_kb = resident_kb_env ? resident_kb_env : (g->n_tile <= 64 ? 90 : 150);
   g->w_resident = (g->n_tiles == 1 && w_img <= (long long)resident_kb * 1024) ? 1 : 0;
+  const bool narrow_streamed = !g->w_resident && g->n_tile <= 64;  // prefers one time tile per item (see above)
   if (g->w_resident) off += (int)w_img;
   g->off_raw = off;
   const int left0 = budget - off;
@@ -167,6 +173,7 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
     if (g->w_resident && cand < 3) continue;
     if (force_mt && mt != force_mt && !g->w_resident) continue;   // tuning aids (VQVS_FORCE_MT / VQVS_FORCE_KBS)
     if (!force_mt && prefer_mt && mt != prefer_mt && !g->w_resident) continue;
+    if (!force_mt && !prefer_mt && narrow_streamed && mt != 1) continue;
     if (force_kbs && kbs != force_kbs) continue;
     if (!sizes_ok(g->nkb_main, kbs) || !sizes_ok(g->nkb_skip, kbs)) continue;
     if (mt * g->acc_cols > 512 || (mt > 1 && (g->n_tile & 31))) continue;

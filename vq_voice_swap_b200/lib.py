@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
-ABI_VERSION = 4
+ABI_VERSION = 5
 RESIZE_NONE, RESIZE_DOWN2, RESIZE_UP2 = 0, 1, 2
 SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
@@ -115,6 +115,11 @@ class ClsHead(C.Structure):
                 ("stem", _p), ("w", _p), ("b", _p), ("logits", _p), ("d_logits", _p), ("d_stem", _p)]
 
 
+class Mfcc(C.Structure):
+    _fields_ = [(n, _i32) for n in "batch t n_fft hop n_bins n_mels n_mfcc frames c_pad ulaw".split()] + \
+               [(n, _p) for n in "x window cos_t sin_t fb dct mfcc out".split()]
+
+
 class Memset(C.Structure):
     _fields_ = [("ptr", _p), ("bytes", _i64)]
 
@@ -154,6 +159,9 @@ SIGNATURES = {
     "vqvs_attnpool_bwd": (C.c_int, [C.POINTER(AttnPool), _p]),
     "vqvs_cls_head_fwd": (C.c_int, [C.POINTER(ClsHead), _p]),
     "vqvs_cls_head_bwd": (C.c_int, [C.POINTER(ClsHead), _p]),
+    "vqvs_mfcc39": (C.c_int, [C.POINTER(Mfcc), _p]),
+    "vqvs_gelu_add": (C.c_int, [_p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "vqvs_deinterleave2": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, C.c_int, _p]),
     "vqvs_keyed_normal": (C.c_int, [_p, C.c_int, C.c_int64, C.c_uint64, C.c_int64, C.c_int32, _p]),
     "vqvs_run": (C.c_int, [C.POINTER(Op), C.c_int, _p]),
     "vqvs_run_timed": (C.c_int, [C.POINTER(Op), C.c_int, _p, C.POINTER(C.c_float)]),
