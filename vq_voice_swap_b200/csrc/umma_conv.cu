@@ -237,17 +237,26 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Optional suspend-time hint (ns) for the probe of a waiting role.  Measured with 2 us and 20 us hints against none on
+// one box (tools/op_profile.py, A/B builds): no difference beyond run-to-run noise, so the default is the plain form.
+#ifndef VQVS_WAIT_HINT_NS
+#define VQVS_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
+#if VQVS_WAIT_HINT_NS > 0
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"((uint32_t)VQVS_WAIT_HINT_NS)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
