@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 5
+#define VQVS_ABI_VERSION 6
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
@@ -237,7 +237,11 @@ int vqvs_ddpm_x0_sum(const float* x_t, const float* eps, const float* coef, int 
 typedef struct VqvsGnBwdPrep { const VqvsGnFinalize* gn; float* prep; /* [5][batch*C] */ } VqvsGnBwdPrep;
 int vqvs_gn_bwd_prep(const VqvsGnFinalize* d, float* prep, void* stream);
 typedef struct VqvsGeluBwd {
-  int32_t batch, c, t, up;   /* up = 1: d_in is [batch,c,t/2] and reaches position i as 0.5*d_in[i/2] (avg_pool1d backward) */
+  int32_t batch, c, t;
+  int32_t up;                /* resize of the FORWARD between gelu(GN(z)) and the conv: 0 none; 1 avg_pool1d (d_in is t/2 long,
+                                reaches i as 0.5*d_in[i/2]); 2 nearest x2 (d_in is 2t long, i collects d_in[2i] + d_in[2i+1]) */
+  int32_t c_total, c_off;    /* the GroupNorm spans c_total concatenated channels, this source is [c_off, c_off + c): prep,
+                                acc and d_in [batch, c_total, .] are indexed with them; z and q are dense [batch, c, t] */
   const float* d_in; const float* z; const float* prep;
   float* q;                  /* [batch,c,t] */
   double* acc;               /* [batch,c,2], zeroed by the caller */
@@ -251,11 +255,17 @@ typedef struct VqvsGnBwdFinalize {
 } VqvsGnBwdFinalize;
 int vqvs_gn_bwd_finalize(const VqvsGnBwdFinalize* d, void* stream);
 typedef struct VqvsAffine3 {
-  int32_t batch, c, t, add_mode;  /* 0: no add, 1: + add[i], 2: + 0.5*add[i/2] (add is [batch,c,t/2]) */
+  int32_t batch, c, t;
+  int32_t add_mode;          /* 0: no add, 1: + add[i], 2: + 0.5*add[i/2] (avg_pool^T), 3: + add[2i] + add[2i+1] (nearest x2 ^T) */
+  int32_t c_total, c_off;    /* coef and add [batch, c_total, .] are indexed like VqvsGeluBwd's d_in */
   const float* q; const float* z; const float* coef; const float* add;
+  const float* add2;         /* optional dense [batch, c, t]: a gradient this tensor already received from another consumer */
   float* out;
 } VqvsAffine3;
 int vqvs_affine3(const VqvsAffine3* d, void* stream);
+/* backward = 0: dst[row, j] = src[row, j*rate] (F.interpolate(h, size = t/rate), nearest -- models/encoder_predictor.py:55-57);
+ * backward = 1: dst[row, j*rate] = src[row, j], zero elsewhere.  t is the LONG length. */
+int vqvs_stride_sample(const float* src, float* dst, int rows, int t, int rate, int backward, void* stream);
 /* Input gradient of Conv1d(1 -> c, k = 3, pad 1) (models/classifier.py:79): dx[n,t] = sum_{c,k} w[c,0,k]*dh[n,c,t+1-k]. */
 typedef struct VqvsConvInBwd { int32_t batch, c, t, pad_; const float* dh; const float* w; float* dx; } VqvsConvInBwd;
 int vqvs_conv_in_bwd(const VqvsConvInBwd* d, void* stream);

@@ -197,6 +197,25 @@ def conv_mfcc():
     save("conv_mfcc.npz", **out)
 
 
+def encoder_predictor():
+    """EncoderPredictor (models/encoder_predictor.py): logits and the guidance gradient VQVAE.decode asks for
+    (vq_vae.py:125-130: d/dx sum(losses * T1))."""
+    from vq_voice_swap.models import EncoderPredictor
+
+    torch.set_grad_enabled(True)
+    m = EncoderPredictor(base_channels=16, downsample_rate=256, num_latents=32, bottleneck_dim=16).eval()
+    synth.load_synth(m, tag="encpred16")
+    x = synth.normal("encpred16/x", (2, 1, 1024)).requires_grad_()
+    ts = torch.tensor([0.7, 0.3])
+    targets = synth.integers("encpred16/targets", (2, 4), 32)
+    logits = m(x, ts)
+    losses = m.losses(x, ts, targets) * targets.shape[-1]
+    grad = torch.autograd.grad(losses.sum(), x)[0]
+    torch.set_grad_enabled(False)
+    save("encoder_predictor16.npz", logits=logits.detach().numpy(), grad=grad.numpy(), losses=losses.detach().numpy(),
+         keys=np.array([f"{k}|{tuple(v.shape)}" for k, v in m.state_dict().items()]))
+
+
 def classifier_small():
     """Classifier logits, the guidance gradient of sample_diffusion.py:34-42, and one guided ddpm_previous."""
     import torch.nn.functional as F
@@ -256,6 +275,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["uncond"]:
         vqvae_uncond()
         sys.exit(0)
+    if sys.argv[1:] == ["encpred"]:
+        encoder_predictor()
+        sys.exit(0)
     if sys.argv[1:] == ["mfcc"]:
         conv_mfcc()
         sys.exit(0)
@@ -266,5 +288,6 @@ if __name__ == "__main__":
     vqvae_small()
     vqvae_uncond()
     conv_mfcc()
+    encoder_predictor()
     classifier_small()
     keys()

@@ -231,14 +231,33 @@ def forward_aten(clf: "Classifier", x: torch.Tensor, ts: torch.Tensor, use_check
 
 
 class EncoderPredictor(Savable):
-    """VQ-code predictor for decode-time guidance (reference models/encoder_predictor.py); optional,
-    off by default in sample_vqvae.py:24-27 and outside the hot path."""
+    """VQ-code predictor for decode-time guidance (reference models/encoder_predictor.py:15-75): a UNetPredictor with
+    `bottleneck_dim` output maps, nearest sampling down to the code rate, and a 1x1 conv to `num_latents` logits.  Forward
+    and the input gradient that VQVAE.decode's `enc_pred` guidance asks for (vq_vae.py:125-130) are libvqvs programs
+    (guidance.PredictorFunction); the cross-entropy on the [N x D x T1] logits is left to torch (a few KB)."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(
-            "EncoderPredictor is not part of the sm_100a sampling path (SURVEY.md section 8f); "
-            "VQVAE.decode accepts any guidance callable evaluated elsewhere"
-        )
+    def __init__(self, base_channels: int, downsample_rate: int, num_latents: int, bottleneck_dim: int = 64):
+        super().__init__()
+        self.base_channels = base_channels
+        self.downsample_rate = downsample_rate
+        self.num_latents = num_latents
+        self.bottleneck_dim = bottleneck_dim
+        self.unet = UNetPredictor(base_channels, out_channels=bottleneck_dim)
+        self.out = nn.Conv1d(bottleneck_dim, num_latents, 1)
+        self._plans = engine.PlanCache()
 
-    def save_kwargs(self):
-        return {}
+    def forward(self, x: torch.Tensor, ts: torch.Tensor, use_checkpoint: bool = False) -> torch.Tensor:
+        """[N x 1 x T], [N] -> logits [N x num_latents x T // downsample_rate]."""
+        from .guidance import PredictorFunction
+
+        if x.shape[-1] % self.downsample_rate:
+            raise ValueError(f"sequence length {x.shape[-1]} must be divisible by the downsample rate {self.downsample_rate}")
+        return PredictorFunction.apply(x, ts, self)
+
+    def losses(self, x: torch.Tensor, ts: torch.Tensor, targets: torch.Tensor, **kwargs) -> torch.Tensor:
+        losses = F.cross_entropy(self(x, ts, **kwargs), targets, reduction="none")
+        return losses.mean(-1)
+
+    def save_kwargs(self) -> Dict[str, Any]:
+        return dict(base_channels=self.base_channels, downsample_rate=self.downsample_rate, num_latents=self.num_latents,
+                    bottleneck_dim=self.bottleneck_dim)

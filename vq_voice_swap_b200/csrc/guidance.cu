@@ -71,20 +71,30 @@ __global__ void gn_bwd_prep_kernel(VqvsGnFinalize d, float* __restrict__ prep) {
 }
 
 // ---- q = d * gelu'(z*S + H) * gf ; acc[row] += (sum q, sum q*zhat) -------------------------------------------------------
+// z / q are dense [batch, c, t]; the GroupNorm may span a channel CONCATENATION of c_total channels of which this source is
+// [c_off, c_off + c): prep / acc and the incoming gradient d_in [batch, c_total, t_d] are indexed through (c_total, c_off).
+// up: 0 = d_in has length t; 1 = the forward avg-pooled (d_in length t/2, reaches i as 0.5*d_in[i/2]);
+//     2 = the forward upsampled x2 (d_in length 2t, position i collects d_in[2i] + d_in[2i+1]).
 constexpr int GB_THREADS = 256, GB_CHUNK = 4096;
 __global__ void __launch_bounds__(GB_THREADS) gelu_bwd_kernel(VqvsGeluBwd d) {
   __shared__ double red[32];
-  const int row = blockIdx.y, total = d.batch * d.c;
-  const float S = d.prep[row], H = d.prep[total + row], mean = d.prep[2 * total + row], rstd = d.prep[3 * total + row],
-              gf = d.prep[4 * total + row];
+  const int row = blockIdx.y, total = d.batch * d.c_total;
+  const int n = row / d.c, prow = n * d.c_total + d.c_off + (row - n * d.c);
+  const float S = d.prep[prow], H = d.prep[total + prow], mean = d.prep[2 * total + prow], rstd = d.prep[3 * total + prow],
+              gf = d.prep[4 * total + prow];
   const float* z = d.z + (size_t)row * d.t;
-  const float* din = d.d_in + (size_t)row * (d.up ? d.t / 2 : d.t);
+  const float* din = d.d_in + (size_t)prow * (d.up == 1 ? d.t / 2 : d.up == 2 ? 2 * d.t : d.t);
   float* q = d.q + (size_t)row * d.t;
   const int t0 = blockIdx.x * GB_CHUNK, t1 = min(d.t, t0 + GB_CHUNK);
   float s1 = 0.f, s2 = 0.f;
   for (int i = t0 + threadIdx.x; i < t1; i += GB_THREADS) {
     const float zz = z[i];
-    const float g = d.up ? 0.5f * din[i >> 1] : din[i];
+    float g;
+    if (d.up == 1) g = 0.5f * din[i >> 1];
+    else if (d.up == 2) {
+      const float2 pr = *reinterpret_cast<const float2*>(din + 2 * i);
+      g = pr.x + pr.y;
+    } else g = din[i];
     const float v = g * gelu_grad(fmaf(zz, S, H)) * gf;
     q[i] = v;
     s1 += v;
@@ -92,8 +102,8 @@ __global__ void __launch_bounds__(GB_THREADS) gelu_bwd_kernel(VqvsGeluBwd d) {
   }
   const double r1 = block_sum((double)s1, red), r2 = block_sum((double)s2, red);
   if (threadIdx.x == 0) {
-    atomicAdd(d.acc + (size_t)row * 2, r1);
-    atomicAdd(d.acc + (size_t)row * 2 + 1, r2);
+    atomicAdd(d.acc + (size_t)prow * 2, r1);
+    atomicAdd(d.acc + (size_t)prow * 2 + 1, r2);
   }
 }
 
@@ -117,19 +127,24 @@ __global__ void gn_bwd_finalize_kernel(VqvsGnBwdFinalize d) {
   d.coef[2 * total + idx] = (float)(-rstd * m1 + rstd * rstd * m2 * mean);
 }
 
-// ---- out = A*q + B*z + C (+ add | + 0.5*add[t/2]) ------------------------------------------------------------------------
+// ---- out = A*q + B*z + C (+ add through resize^T) (+ add2) ----------------------------------------------------------------
+// coef and add [batch, c_total, t_add] are indexed through (c_total, c_off) like vqvs_gelu_bwd's d_in; add2 is dense.
 __global__ void __launch_bounds__(GB_THREADS) affine3_kernel(VqvsAffine3 d) {
-  const int row = blockIdx.y, total = d.batch * d.c;
-  const float A = d.coef[row], B = d.coef[total + row], Cc = d.coef[2 * total + row];
+  const int row = blockIdx.y, total = d.batch * d.c_total;
+  const int n = row / d.c, prow = n * d.c_total + d.c_off + (row - n * d.c);
+  const float A = d.coef[prow], B = d.coef[total + prow], Cc = d.coef[2 * total + prow];
   const float* q = d.q + (size_t)row * d.t;
   const float* z = d.z + (size_t)row * d.t;
-  const float* add = d.add ? d.add + (size_t)row * (d.add_mode == 2 ? d.t / 2 : d.t) : nullptr;
+  const float* add = d.add ? d.add + (size_t)prow * (d.add_mode == 2 ? d.t / 2 : d.add_mode == 3 ? 2 * d.t : d.t) : nullptr;
+  const float* add2 = d.add2 ? d.add2 + (size_t)row * d.t : nullptr;
   float* out = d.out + (size_t)row * d.t;
   const int t0 = blockIdx.x * GB_CHUNK, t1 = min(d.t, t0 + GB_CHUNK);
   for (int i = t0 + threadIdx.x; i < t1; i += GB_THREADS) {
     float v = fmaf(A, q[i], fmaf(B, z[i], Cc));
     if (d.add_mode == 1) v += add[i];
     else if (d.add_mode == 2) v += 0.5f * add[i >> 1];
+    else if (d.add_mode == 3) v += add[2 * i] + add[2 * i + 1];
+    if (add2) v += add2[i];
     out[i] = v;
   }
 }
@@ -306,9 +321,31 @@ __global__ void cls_head_bwd_kernel(VqvsClsHead d) {
   }
 }
 
+// ---- backward of h[:, :, j*rate] sampling (F.interpolate(h, size = t / rate), nearest): dh[j*rate] = d[j], zero elsewhere ----
+__global__ void scatter_stride_kernel(const float* __restrict__ d, float* __restrict__ out, int t, int rate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t row = blockIdx.y;
+  if (i >= t) return;
+  out[row * t + i] = (i % rate == 0) ? d[row * (t / rate) + i / rate] : 0.f;
+}
+__global__ void gather_stride_kernel(const float* __restrict__ h, float* __restrict__ out, int t, int rate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t row = blockIdx.y;
+  if (j >= t / rate) return;
+  out[row * (t / rate) + j] = h[row * t + (size_t)j * rate];
+}
+
 }  // namespace vqvs
 
 using namespace vqvs;
+
+extern "C" int vqvs_stride_sample(const float* src, float* dst, int rows, int t, int rate, int backward, void* stream) {
+  VQVS_CHECK_ARG(src && dst && rows > 0 && rows <= 65535 && t > 0 && rate > 0 && t % rate == 0, "stride_sample: bad arguments");
+  if (backward) scatter_stride_kernel<<<dim3(ceil_div(t, 256), rows), 256, 0, (cudaStream_t)stream>>>(src, dst, t, rate);
+  else gather_stride_kernel<<<dim3(ceil_div(t / rate, 256), rows), 256, 0, (cudaStream_t)stream>>>(src, dst, t, rate);
+  VQVS_CHECK_LAUNCH("vqvs_stride_sample");
+  return VQVS_OK;
+}
 
 extern "C" int vqvs_gn_bwd_prep(const VqvsGnFinalize* d, float* prep, void* stream) {
   VQVS_CHECK_ARG(d && prep && d->batch > 0 && d->groups > 0 && (d->c_a + d->c_b) % d->groups == 0 && d->count > 0,
@@ -322,8 +359,9 @@ extern "C" int vqvs_gn_bwd_prep(const VqvsGnFinalize* d, float* prep, void* stre
 
 extern "C" int vqvs_gelu_bwd(const VqvsGeluBwd* d, void* stream) {
   VQVS_CHECK_ARG(d && d->batch > 0 && d->c > 0 && d->t > 0 && (long long)d->batch * d->c <= 65535, "gelu_bwd: bad sizes");
+  VQVS_CHECK_ARG(d->c_total >= d->c && d->c_off >= 0 && d->c_off + d->c <= d->c_total, "gelu_bwd: bad channel window");
   VQVS_CHECK_ARG(d->d_in && d->z && d->prep && d->q && d->acc, "gelu_bwd: null pointer");
-  VQVS_CHECK_ARG(!d->up || (d->t & 1) == 0, "gelu_bwd: pooled gradient needs an even length");
+  VQVS_CHECK_ARG(d->up >= 0 && d->up <= 2 && (d->up != 1 || (d->t & 1) == 0), "gelu_bwd: bad resize mode / odd pooled length");
   dim3 grid(ceil_div(d->t, GB_CHUNK), d->batch * d->c);
   gelu_bwd_kernel<<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>(*d);
   VQVS_CHECK_LAUNCH("vqvs_gelu_bwd");
@@ -340,8 +378,9 @@ extern "C" int vqvs_gn_bwd_finalize(const VqvsGnBwdFinalize* d, void* stream) {
 
 extern "C" int vqvs_affine3(const VqvsAffine3* d, void* stream) {
   VQVS_CHECK_ARG(d && d->batch > 0 && d->c > 0 && d->t > 0 && (long long)d->batch * d->c <= 65535, "affine3: bad sizes");
-  VQVS_CHECK_ARG(d->q && d->z && d->coef && d->out && d->add_mode >= 0 && d->add_mode <= 2 && (d->add_mode == 0 || d->add),
+  VQVS_CHECK_ARG(d->q && d->z && d->coef && d->out && d->add_mode >= 0 && d->add_mode <= 3 && (d->add_mode == 0 || d->add),
                  "affine3: bad arguments");
+  VQVS_CHECK_ARG(d->c_total >= d->c && d->c_off >= 0 && d->c_off + d->c <= d->c_total, "affine3: bad channel window");
   VQVS_CHECK_ARG(d->add_mode != 2 || (d->t & 1) == 0, "affine3: pooled skip gradient needs an even length");
   dim3 grid(ceil_div(d->t, GB_CHUNK), d->batch * d->c);
   affine3_kernel<<<grid, GB_THREADS, 0, (cudaStream_t)stream>>>(*d);

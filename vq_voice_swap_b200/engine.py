@@ -432,7 +432,10 @@ def _predictor_blocks(net):
     return list(net.down_blocks) + list(net.middle_blocks) + list(net.up_blocks)
 
 
-def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend: str) -> Plan:
+def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend: str, keep_activations: bool = False) -> Plan:
+    """keep_activations: every block gets its own intra-block and output buffers and the plan records
+    `plan.saved = [(block, [source Acts], u, out, resize mode)]` plus `plan.head` -- what a backward program needs
+    (guidance.PredictorGuidancePlans); sampling plans reuse three buffers instead."""
     rate = net.downsample_rate
     if t % rate:
         raise ValueError(f"sequence length {t} must be divisible by the UNet downsample rate {rate}")
@@ -441,9 +444,10 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
     device = next(net.parameters()).device
     _check_module(net)
     blocks = _predictor_blocks(net)
-    w = weights_for(net, blocks, backend, reduced_precision=True)
+    w = weights_for(net, blocks, backend, reduced_precision=not keep_activations)
     plan = Plan(device, batch, backend)
     plan.weights = w
+    plan.saved = []
     bc = net.base_channels
     emb_dim = 4 * bc
 
@@ -455,8 +459,8 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
         max(b.out_channels * _resized(t_l, resize_mode(b.scale_factor)) for b, t_l in _walk_lengths(net, t)),
         bc * t,
     )
-    ping = [plan.empty(max_elems), plan.empty(max_elems)]
-    h1_buf = plan.empty(max_elems)
+    ping = [plan.empty(max_elems), plan.empty(max_elems)] if not keep_activations else None
+    h1_buf = plan.empty(max_elems) if not keep_activations else None
 
     # inputs that change per call are patched into these structs
     plan.ts = plan.empty(batch)
@@ -501,29 +505,39 @@ def build_predictor_plan(net, batch: int, t: int, t_cond: Optional[int], backend
     ci.out, ci.stats_out = h.ptr, h.stats_ptr
     plan.add(L.OP_CONV_IN, ci, "conv_in")
 
+    plan.h0 = h
     skips = [h]
     cur_t = t
+    own = keep_activations  # True: no buffer is ever reused
     for blk in net.down_blocks:
-        t_out = _resized(cur_t, resize_mode(blk.scale_factor))
-        h1 = alloc.act(blk.out_channels, t_out, h1_buf)
+        mode = resize_mode(blk.scale_factor)
+        t_out = _resized(cur_t, mode)
+        h1 = alloc.act(blk.out_channels, t_out, None if own else h1_buf)
         out = alloc.act(blk.out_channels, t_out)
         _emit_block(plan, blk, [h], h1, out, w, scratch, plan.ab)
+        plan.saved.append((blk, [h], h1, out, mode))
         h, cur_t = out, t_out
         skips.append(h)
     flip = 0
     for blk in net.middle_blocks:
-        h1 = alloc.act(blk.out_channels, cur_t, h1_buf)
-        out = alloc.act(blk.out_channels, cur_t, ping[flip])
+        h1 = alloc.act(blk.out_channels, cur_t, None if own else h1_buf)
+        out = alloc.act(blk.out_channels, cur_t, None if own else ping[flip])
         _emit_block(plan, blk, [h], h1, out, w, scratch, plan.ab)
+        plan.saved.append((blk, [h], h1, out, L.RESIZE_NONE))
         h, flip = out, flip ^ 1
     period = net.depth_mult + 2
     for i, blk in enumerate(net.up_blocks):
         srcs = [h] if i % period == period - 1 else [h, skips.pop()]
-        t_out = _resized(cur_t, resize_mode(blk.scale_factor))
-        h1 = alloc.act(blk.out_channels, t_out, h1_buf)
-        out = alloc.act(blk.out_channels, t_out, ping[flip])
+        mode = resize_mode(blk.scale_factor)
+        t_out = _resized(cur_t, mode)
+        h1 = alloc.act(blk.out_channels, t_out, None if own else h1_buf)
+        out = alloc.act(blk.out_channels, t_out, None if own else ping[flip])
         _emit_block(plan, blk, srcs, h1, out, w, scratch, plan.ab)
+        plan.saved.append((blk, srcs, h1, out, mode))
         h, cur_t, flip = out, t_out, flip ^ 1
+    plan.h_last = h
+    if not own:
+        plan.saved = []
 
     head_gn, head_conv = net.out[0][0], net.out[1]
     _emit_gn(plan, [h], head_gn, scratch[0], scratch[1])

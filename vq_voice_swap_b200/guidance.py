@@ -1,22 +1,24 @@
-"""Classifier guidance without ATen: forward and input-gradient programs of reference models/classifier.py.
+"""Guidance gradients without ATen: forward and input-gradient programs of the reference's guidance models.
 
-`cond_fn` of reference sample_diffusion.py:34-42 asks for d log p(label | x_t, t) / d x_t through `torch.autograd.grad`.
-`ClassifierFunction` is a torch.autograd.Function whose forward runs the guidance model as one libvqvs program
-(time embedding, FiLM table, input conv, 27 FiLM ResBlocks on the tcgen05 conv kernel, GroupNorm/GELU, attention pool,
-Linear head) keeping every block's input x and intra-block tensor u resident, and whose backward runs a second program:
+`cond_fn` of reference sample_diffusion.py:34-42 asks for d log p(label | x_t, t) / d x_t, and VQVAE.decode's
+`enc_pred` guidance (vq_vae.py:125-130) for the gradient of EncoderPredictor.losses, both through `torch.autograd.grad`.
+`ClassifierFunction` / `PredictorFunction` are torch.autograd.Functions whose forward runs the model as one libvqvs
+program (every block's inputs x and intra-block tensor u stay resident) and whose backward runs a second program:
 
-    d_logits -> head^T -> attention-pool^T -> [GELU, GroupNorm]^T -> for each ResBlock, last to first:
+    for each ResBlock, last to first (reference models/unet.py:307-316 differentiated):
         dw  = conv2^T(dy)                      vqvs_conv1d_umma, weights transposed + taps flipped, same dilation
         du  = [GELU, FiLM, GN_b]^T(dw; u)      vqvs_gelu_bwd -> vqvs_gn_bwd_finalize -> vqvs_affine3
         dp  = conv1^T(du)                      vqvs_conv1d_umma
         dx  = [GELU, GN_a]^T(resize^T dp; x) + resize^T(skip^T(dy))      (skip^T = identity or the transposed 1x1 conv)
-    -> input conv^T -> dx [N, 1, T]
+    A block fed by a channel concatenation (the UNet's up path) splits dp / the skip gradient by channel window; a tensor
+    with two consumers (the UNet's skip stack) accumulates both gradients (VqvsAffine3.add2).
 
-No ATen kernel and no autograd graph is involved in either direction; torch only owns the memory and the stream.
+The classifier adds attention-pool^T and head^T in front and the input conv^T behind; the predictor adds the head conv^T
+and (for EncoderPredictor) the strided sampling + 1x1 output conv.  No ATen kernel and no autograd graph is involved in
+either direction; torch only owns the memory and the stream.
 """
 
 import ctypes as C
-import math
 from typing import List, Optional
 
 import torch
@@ -31,8 +33,147 @@ def _pack_transposed(weight: torch.Tensor) -> Optional[engine.Packed]:
     return engine.pack_weights(wt, None, L.PREC_BF16X3)
 
 
-class GuidancePlans:
-    """Forward + backward launch programs of one Classifier for one (batch, length)."""
+class Backward:
+    """Emits the input-gradient program of a chain / DAG of ResBlocks into an engine.Plan."""
+
+    def __init__(self, plan: engine.Plan, batch: int, saved, film_ab: Optional[torch.Tensor], film_offsets, film_total: int,
+                 extra_elems: int = 0):
+        self.plan, self.batch = plan, batch
+        self.film_ab, self.film_offsets, self.film_total = film_ab, film_offsets, film_total
+        c_max = 16
+        elems = extra_elems
+        n_gn = 2
+        for _, srcs, u, out, _ in saved:
+            c_in = sum(s.c for s in srcs)
+            c_max = max(c_max, c_in, out.c)
+            elems = max(elems, c_in * max(srcs[0].t, out.t), out.c * out.t)
+            n_gn += 2
+        self.c_max = c_max
+        self.acc = plan.empty(n_gn * batch * c_max * 2, dtype=torch.float64)
+        engine._memset_op(plan, self.acc)
+        self.acc_used = 0
+        self.prep = plan.empty(5 * batch * c_max)
+        self.coef = plan.empty(3 * batch * c_max)
+        self.scratch = [plan.empty(batch * elems) for _ in range(4)]  # dw/du, dp, skip^T(dy), q
+        self.grads = {}     # id(Act) -> gradient tensor [batch, c, t]
+        self.packed = []    # keep the transposed weight images alive
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def grad_of(self, act) -> torch.Tensor:
+        g = self.grads.get(id(act))
+        if g is None:
+            raise RuntimeError("backward reached a tensor that has no gradient yet (blocks must be visited last to first)")
+        return g
+
+    def _next_acc(self) -> torch.Tensor:
+        n = self.batch * self.c_max * 2
+        view = self.acc[self.acc_used:self.acc_used + n]
+        self.acc_used += n
+        assert self.acc_used <= self.acc.numel()
+        return view
+
+    def conv_t(self, src_ptr: int, c_in: int, c_out: int, t: int, ksize: int, dilation: int, weight: torch.Tensor, dst_ptr: int):
+        packed = _pack_transposed(weight)
+        if packed is None:
+            raise ValueError(f"transposed conv {c_in}->{c_out}: channel counts must be multiples of 16")
+        self.packed.append(packed)
+        d = L.Conv()
+        d.batch, d.c_a, d.c_b, d.t_in, d.c_out, d.t_out = self.batch, c_in, 0, t, c_out, t
+        d.ksize, d.dilation, d.resize, d.act, d.skip_mode = ksize, dilation, L.RESIZE_NONE, 0, L.SKIP_NONE
+        d.xa, d.out = src_ptr, dst_ptr
+        d.w_packed = packed.img.data_ptr()
+        d.reserved_ = packed.prec << L.CONV_PREC_SHIFT
+        if not L.load().vqvs_conv1d_umma_supported(C.byref(d)):
+            raise ValueError(f"transposed conv {c_in}->{c_out} k={ksize}: shape not supported by the tcgen05 kernel")
+        self.plan.add(L.OP_CONV_UMMA, d)
+
+    def gn_backward(self, fin, d_in_ptr: int, srcs: List, up: int, outs: List[torch.Tensor], add_ptr: int = 0, add_mode: int = 0):
+        """[GELU, (FiLM), GroupNorm]^T over the channel concatenation of `srcs`.
+
+        d_in [batch, sum c, t_d]: gradient w.r.t. resize(gelu(GN(cat(srcs)))); outs[k] receives d(srcs[k]) (and is ADDED to
+        when that tensor already holds a gradient from another consumer); add: the skip path's gradient, same layout as d_in."""
+        plan, batch = self.plan, self.batch
+        c_total = sum(s.c for s in srcs)
+        pp = L.GnBwdPrep()
+        pp.gn, pp.prep = C.addressof(fin), self.prep.data_ptr()
+        plan.add(L.OP_GN_BWD_PREP, pp)
+        acc = self._next_acc()
+        off = 0
+        qs = []
+        for k, s in enumerate(srcs):
+            q = self.scratch[3] if len(srcs) == 1 else plan.empty(batch * s.c * s.t)
+            qs.append(q)
+            gb = L.GeluBwd()
+            gb.batch, gb.c, gb.t, gb.up, gb.c_total, gb.c_off = batch, s.c, s.t, up, c_total, off
+            gb.d_in, gb.z, gb.prep, gb.q, gb.acc = d_in_ptr, s.ptr, self.prep.data_ptr(), q.data_ptr(), acc.data_ptr()
+            plan.add(L.OP_GELU_BWD, gb)
+            off += s.c
+        gf = L.GnBwdFinalize()
+        gf.batch, gf.c, gf.groups, gf.count = batch, c_total, fin.groups, srcs[0].t
+        gf.acc, gf.prep, gf.coef = acc.data_ptr(), self.prep.data_ptr(), self.coef.data_ptr()
+        plan.add(L.OP_GN_BWD_FINALIZE, gf)
+        off = 0
+        for k, s in enumerate(srcs):
+            af = L.Affine3()
+            af.batch, af.c, af.t, af.add_mode, af.c_total, af.c_off = batch, s.c, s.t, add_mode, c_total, off
+            af.q, af.z, af.coef, af.add = qs[k].data_ptr(), s.ptr, self.coef.data_ptr(), add_ptr
+            prev = self.grads.get(id(s))
+            af.add2 = prev.data_ptr() if prev is not None else 0
+            af.out = outs[k].data_ptr()
+            plan.add(L.OP_AFFINE3, af)
+            self.grads[id(s)] = outs[k]
+            off += s.c
+
+    # -- one ResBlock ----------------------------------------------------------------------------
+    def block(self, blk, srcs: List, u, out, mode: int):
+        plan, batch = self.plan, self.batch
+        dy = self.grad_of(out)
+        bw, bp, bs = self.scratch[0], self.scratch[1], self.scratch[2]
+        c_in = sum(s.c for s in srcs)
+        conv1, conv2, proj = blk.pre_cond[2], engine._tail_conv(blk), engine._skip_proj(blk)
+        # dw = conv2^T(dy); du = [GELU, FiLM, GN_b]^T(dw; u), in place
+        self.conv_t(dy.data_ptr(), out.c, out.c, out.t, 3, conv2.dilation[0], conv2.weight, bw.data_ptr())
+        film_ptr = film_stride = 0
+        if getattr(blk, "emb_channels", None):
+            film_ptr = self.film_ab.data_ptr() + 4 * self.film_offsets[id(blk)]
+            film_stride = self.film_total
+        fin_b = engine._emit_gn(plan, [u], blk.pre_cond[3], self.prep, self.prep, film_ptr, film_stride, standalone=False)
+        du = bw[: batch * u.c * u.t].view(batch, u.c, u.t)
+        saved_grad = self.grads.pop(id(u), None)  # u never has another consumer
+        self.gn_backward(fin_b, bw.data_ptr(), [u], 0, [du])
+        self.grads.pop(id(u), None)
+        assert saved_grad is None
+        # dp = conv1^T(du): gradient w.r.t. resize(gelu(GN_a(cat(srcs)))), length t_out
+        self.conv_t(bw.data_ptr(), out.c, c_in, out.t, 3, 1, conv1.weight, bp.data_ptr())
+        # skip path: ds = dy or skip^T(dy), length t_out, reaches the sources through resize^T
+        if proj is not None:
+            self.conv_t(dy.data_ptr(), out.c, c_in, out.t, 1, 1, proj.weight, bs.data_ptr())
+            add = bs.data_ptr()
+        else:
+            add = dy.data_ptr()
+        up = 1 if mode == L.RESIZE_DOWN2 else 2 if mode == L.RESIZE_UP2 else 0
+        add_mode = 2 if mode == L.RESIZE_DOWN2 else 3 if mode == L.RESIZE_UP2 else 1
+        fin_a = engine._emit_gn(plan, srcs, blk.pre_cond[0][0], self.prep, self.prep, standalone=False)
+        outs = []
+        for s in srcs:
+            prev = self.grads.get(id(s))
+            outs.append(prev if prev is not None else plan.empty(batch, s.c, s.t))
+        self.gn_backward(fin_a, bp.data_ptr(), srcs, up, outs, add_ptr=add, add_mode=add_mode)
+
+
+class _Plans:
+    """Shared forward/backward bookkeeping: one forward, then (at most) its own backward."""
+
+    generation = 0
+
+    def _check_generation(self, generation: int):
+        if generation != self.generation:
+            raise RuntimeError("the model was evaluated again before this backward: its saved activations are gone "
+                               "(one forward, then its backward -- the pattern of sample_diffusion.py's cond_fn)")
+
+
+class GuidancePlans(_Plans):
+    """Forward + backward launch programs of one Classifier (reference models/classifier.py) for one (batch, length)."""
 
     def __init__(self, clf, batch: int, t: int, backend: str):
         stem = clf.stem
@@ -69,6 +210,7 @@ class GuidancePlans:
         fwd.add(L.OP_FILM, fl)
 
         h = alloc.act(bc, t)
+        self.h0 = h
         ci = L.ConvIn()
         ci.batch, ci.c_out, ci.t, ci.t_cond = batch, bc, t, 0
         ci.w, ci.bias = L.ptr(stem.in_conv.weight), L.ptr(stem.in_conv.bias)
@@ -76,7 +218,7 @@ class GuidancePlans:
         fwd.add(L.OP_CONV_IN, ci, "conv_in")
 
         # every block keeps its input x and its intra-block tensor u: the backward program reads both
-        self.saved = []  # (block, x Act, u Act, out Act, resize mode)
+        self.saved = []
         cur_t = t
         for blk in blocks:
             mode = engine.resize_mode(blk.scale_factor)
@@ -84,7 +226,7 @@ class GuidancePlans:
             u = alloc.act(blk.out_channels, t_out)
             out = alloc.act(blk.out_channels, t_out)
             engine._emit_block(fwd, blk, [h], u, out, w, scratch, fwd.ab)
-            self.saved.append((blk, h, u, out, mode))
+            self.saved.append((blk, [h], u, out, mode))
             h, cur_t = out, t_out
         self.h_last, self.t_last = h, cur_t
 
@@ -96,134 +238,58 @@ class GuidancePlans:
         pp = L.GnBwdPrep()
         pp.gn, pp.prep = C.addressof(self.fin_final), self.prep_final.data_ptr()
         fwd.add(L.OP_GN_BWD_PREP, pp)
-        heads = pool.num_heads
-        ws_bytes = L.load().vqvs_attnpool_workspace_bytes(batch, c_last, cur_t, heads)
+        ws_bytes = L.load().vqvs_attnpool_workspace_bytes(batch, c_last, cur_t, pool.num_heads)
         if ws_bytes <= 0:
             raise ValueError("attention pool: unsupported shape")
         self.ap_ws = fwd.empty(ws_bytes // 4)
         self.stem_out = fwd.empty(batch, stem.out_channels)
-        ap = L.AttnPool()
-        ap.batch, ap.c, ap.t, ap.heads, ap.c_out = batch, c_last, cur_t, heads, stem.out_channels
-        ap.h, ap.prep = h.ptr, self.prep_final.data_ptr()
-        ap.w_qkv, ap.b_qkv = L.ptr(pool.qkv_proj.weight), L.ptr(pool.qkv_proj.bias)
-        ap.w_proj, ap.b_proj = L.ptr(pool.c_proj.weight), L.ptr(pool.c_proj.bias)
-        ap.ws, ap.out = self.ap_ws.data_ptr(), self.stem_out.data_ptr()
-        fwd.add(L.OP_ATTNPOOL_FWD, ap)
-        head = clf.out[1]
+        fwd.add(L.OP_ATTNPOOL_FWD, self._attnpool())
         self.logits = fwd.empty(batch, clf.num_labels)
-        hd = L.ClsHead()
-        hd.batch, hd.dim, hd.labels = batch, stem.out_channels, clf.num_labels
-        hd.stem, hd.w, hd.b = self.stem_out.data_ptr(), L.ptr(head.weight), L.ptr(head.bias)
-        hd.logits = self.logits.data_ptr()
-        fwd.add(L.OP_CLS_HEAD_FWD, hd)
+        fwd.add(L.OP_CLS_HEAD_FWD, self._head())
         self.fwd = fwd.compile()
-        self.generation = 0
         self._build_backward(w, backend)
 
-    # -----------------------------------------------------------------------------------------
-    def _build_backward(self, w, backend):
-        clf, stem, batch = self.clf, self.clf.stem, self.batch
-        bwd = engine.Plan(self.device, batch, backend)
-        saved = self.saved
-        c_max = max(max(x.c, out.c) for _, x, _, out, _ in saved)
-        n_gn = 2 * len(saved) + 1
-        acc = bwd.empty(n_gn * batch * c_max * 2, dtype=torch.float64)
-        engine._memset_op(bwd, acc)
-        prep = bwd.empty(5 * batch * c_max)
-        coef = bwd.empty(3 * batch * c_max)
-        max_elems = batch * max(max(x.c * x.t, out.c * out.t) for _, x, _, out, _ in saved)
-        bufs = [bwd.empty(max_elems) for _ in range(4)]
-        self.d_logits = bwd.empty(batch, clf.num_labels)
-        d_stem = bwd.empty(batch, stem.out_channels)
-        self.dx = bwd.empty(batch, 1, self.t)
-        acc_slot = [0]
-
-        def next_acc(c):
-            view = acc[acc_slot[0]:acc_slot[0] + batch * c * 2]
-            acc_slot[0] += batch * c_max * 2
-            return view
-
-        def gn_backward(fin, d_in, z, c, t, up, q_out, out, add=None, add_mode=0):
-            """[GELU, (FiLM), GroupNorm]^T: out = d(z) given d_in = gradient w.r.t. gelu(GN(z))."""
-            pp = L.GnBwdPrep()
-            pp.gn, pp.prep = C.addressof(fin), prep.data_ptr()
-            bwd.add(L.OP_GN_BWD_PREP, pp)
-            a = next_acc(c)
-            gb = L.GeluBwd()
-            gb.batch, gb.c, gb.t, gb.up = batch, c, t, up
-            gb.d_in, gb.z, gb.prep, gb.q, gb.acc = d_in, z, prep.data_ptr(), q_out, a.data_ptr()
-            bwd.add(L.OP_GELU_BWD, gb)
-            gf = L.GnBwdFinalize()
-            gf.batch, gf.c, gf.groups, gf.count = batch, c, fin.groups, t
-            gf.acc, gf.prep, gf.coef = a.data_ptr(), prep.data_ptr(), coef.data_ptr()
-            bwd.add(L.OP_GN_BWD_FINALIZE, gf)
-            af = L.Affine3()
-            af.batch, af.c, af.t, af.add_mode = batch, c, t, add_mode
-            af.q, af.z, af.coef, af.add, af.out = q_out, z, coef.data_ptr(), add or 0, out
-            bwd.add(L.OP_AFFINE3, af)
-
-        def conv_t(src_ptr, c_in, c_out, t, ksize, dilation, packed, dst_ptr):
-            d = L.Conv()
-            d.batch, d.c_a, d.c_b, d.t_in, d.c_out, d.t_out = batch, c_in, 0, t, c_out, t
-            d.ksize, d.dilation, d.resize, d.act, d.skip_mode = ksize, dilation, L.RESIZE_NONE, 0, L.SKIP_NONE
-            d.xa, d.out = src_ptr, dst_ptr
-            d.w_packed = packed.img.data_ptr()
-            d.reserved_ = packed.prec << L.CONV_PREC_SHIFT
-            if not L.load().vqvs_conv1d_umma_supported(C.byref(d)):
-                raise ValueError(f"transposed conv {c_in}->{c_out} k={ksize}: shape not supported by the tcgen05 kernel")
-            bwd.add(L.OP_CONV_UMMA, d)
-
-        # head^T, attention pool^T
-        head = clf.out[1]
-        hd = L.ClsHead()
-        hd.batch, hd.dim, hd.labels = batch, stem.out_channels, clf.num_labels
-        hd.stem, hd.w, hd.b = self.stem_out.data_ptr(), L.ptr(head.weight), L.ptr(head.bias)
-        hd.d_logits, hd.d_stem = self.d_logits.data_ptr(), d_stem.data_ptr()
-        bwd.add(L.OP_CLS_HEAD_BWD, hd)
-        pool = stem.out[1]
-        c_last, t_last = self.h_last.c, self.t_last
+    def _attnpool(self) -> L.AttnPool:
+        pool, stem = self.clf.stem.out[1], self.clf.stem
         ap = L.AttnPool()
-        ap.batch, ap.c, ap.t, ap.heads, ap.c_out = batch, c_last, t_last, pool.num_heads, stem.out_channels
+        ap.batch, ap.c, ap.t, ap.heads, ap.c_out = self.batch, self.h_last.c, self.t_last, pool.num_heads, stem.out_channels
         ap.h, ap.prep = self.h_last.ptr, self.prep_final.data_ptr()
         ap.w_qkv, ap.b_qkv = L.ptr(pool.qkv_proj.weight), L.ptr(pool.qkv_proj.bias)
         ap.w_proj, ap.b_proj = L.ptr(pool.c_proj.weight), L.ptr(pool.c_proj.bias)
-        ap.ws, ap.d_out, ap.d_act = self.ap_ws.data_ptr(), d_stem.data_ptr(), bufs[1].data_ptr()
-        bwd.add(L.OP_ATTNPOOL_BWD, ap)
-        # final GroupNorm + GELU: gradient w.r.t. the last block's output lands in bufs[0]
-        gn_backward(self.fin_final, bufs[1].data_ptr(), self.h_last.ptr, c_last, t_last, 0, bufs[1].data_ptr(), bufs[0].data_ptr())
-        dy = 0  # index of the buffer holding the current gradient
+        ap.ws, ap.out = self.ap_ws.data_ptr(), self.stem_out.data_ptr()
+        return ap
 
-        self.packed_t = []
-        for blk, x, u, out, mode in reversed(saved):
-            free = [i for i in range(4) if i != dy]
-            b_w, b_p, b_q = free
-            pool_blk = mode == L.RESIZE_DOWN2
-            conv1, conv2, proj = blk.pre_cond[2], engine._tail_conv(blk), engine._skip_proj(blk)
-            pk2, pk1 = _pack_transposed(conv2.weight), _pack_transposed(conv1.weight)
-            pks = _pack_transposed(proj.weight) if proj is not None else None
-            self.packed_t += [pk2, pk1, pks]
-            # dw = conv2^T(dy); du = [GELU, FiLM, GN_b]^T(dw; u), in place
-            conv_t(bufs[dy].data_ptr(), out.c, out.c, out.t, 3, conv2.dilation[0], pk2, bufs[b_w].data_ptr())
-            film_ptr = self.fwd.ab.data_ptr() + 4 * self.fwd.weights.film_offsets[id(blk)]
-            fin_b = engine._emit_gn(bwd, [u], blk.pre_cond[3], prep, prep, film_ptr, self.fwd.weights.film_total, standalone=False)
-            gn_backward(fin_b, bufs[b_w].data_ptr(), u.ptr, u.c, u.t, 0, bufs[b_w].data_ptr(), bufs[b_w].data_ptr())
-            # dp = conv1^T(du)
-            conv_t(bufs[b_w].data_ptr(), out.c, x.c, out.t, 3, 1, pk1, bufs[b_p].data_ptr())
-            # skip path: ds = dy or skip^T(dy) (length t_out), reaches x through resize^T
-            if pks is not None:
-                conv_t(bufs[dy].data_ptr(), out.c, x.c, out.t, 1, 1, pks, bufs[b_w].data_ptr())
-                add = bufs[b_w].data_ptr()
-            else:
-                add = bufs[dy].data_ptr()
-            # dx = [GELU, GN_a]^T(resize^T dp; x) + resize^T ds
-            fin_a = engine._emit_gn(bwd, [x], blk.pre_cond[0][0], prep, prep, standalone=False)
-            gn_backward(fin_a, bufs[b_p].data_ptr(), x.ptr, x.c, x.t, 1 if pool_blk else 0, bufs[b_q].data_ptr(), bufs[b_q].data_ptr(),
-                        add=add, add_mode=2 if pool_blk else 1)
-            dy = b_q
+    def _head(self) -> L.ClsHead:
+        head = self.clf.out[1]
+        hd = L.ClsHead()
+        hd.batch, hd.dim, hd.labels = self.batch, self.clf.stem.out_channels, self.clf.num_labels
+        hd.stem, hd.w, hd.b = self.stem_out.data_ptr(), L.ptr(head.weight), L.ptr(head.bias)
+        hd.logits = self.logits.data_ptr()
+        return hd
+
+    def _build_backward(self, w, backend):
+        clf, stem, batch = self.clf, self.clf.stem, self.batch
+        bwd = engine.Plan(self.device, batch, backend)
+        c_last, t_last = self.h_last.c, self.t_last
+        bk = Backward(bwd, batch, self.saved, self.fwd.ab, w.film_offsets, w.film_total, extra_elems=c_last * t_last)
+        self.d_logits = bwd.empty(batch, clf.num_labels)
+        d_stem = bwd.empty(batch, stem.out_channels)
+        self.dx = bwd.empty(batch, 1, self.t)
+        hd = self._head()
+        hd.d_logits, hd.d_stem = self.d_logits.data_ptr(), d_stem.data_ptr()
+        bwd.add(L.OP_CLS_HEAD_BWD, hd)
+        d_act = bwd.empty(batch, c_last, t_last)
+        ap = self._attnpool()
+        ap.d_out, ap.d_act = d_stem.data_ptr(), d_act.data_ptr()
+        bwd.add(L.OP_ATTNPOOL_BWD, ap)
+        bk.gn_backward(self.fin_final, d_act.data_ptr(), [self.h_last], 0, [bwd.empty(batch, c_last, t_last)])
+        for blk, srcs, u, out, mode in reversed(self.saved):
+            bk.block(blk, srcs, u, out, mode)
         cb = L.ConvInBwd()
         cb.batch, cb.c, cb.t = batch, stem.base_channels, self.t
-        cb.dh, cb.w, cb.dx = bufs[dy].data_ptr(), L.ptr(stem.in_conv.weight), self.dx.data_ptr()
+        cb.dh, cb.w, cb.dx = bk.grad_of(self.h0).data_ptr(), L.ptr(stem.in_conv.weight), self.dx.data_ptr()
         bwd.add(L.OP_CONV_IN_BWD, cb)
+        self.bk = bk
         self.bwd = bwd.compile()
 
     # -----------------------------------------------------------------------------------------
@@ -235,19 +301,104 @@ class GuidancePlans:
         self.generation += 1
         return self.logits.clone()
 
-    def stem_features(self) -> torch.Tensor:
-        return self.stem_out.clone()
-
     def backward(self, d_logits: torch.Tensor, generation: int) -> torch.Tensor:
-        if generation != self.generation:
-            raise RuntimeError("the classifier was evaluated again before this backward: its saved activations are gone "
-                               "(one forward, then its backward -- the pattern of sample_diffusion.py's cond_fn)")
+        self._check_generation(generation)
         self.d_logits.copy_(d_logits.to(self.d_logits), non_blocking=True)
         self.bwd.run()
         return self.dx.clone()
 
 
-def plans_for(clf, x: torch.Tensor) -> GuidancePlans:
+class PredictorGuidancePlans(_Plans):
+    """Forward + backward programs of a UNetPredictor with `out_channels` feature maps, optionally followed by the strided
+    sampling and 1x1 conv of EncoderPredictor (reference models/encoder_predictor.py:40-59)."""
+
+    def __init__(self, net, batch: int, t: int, backend: str, rate: int = 1, out_conv: Optional[torch.nn.Conv1d] = None):
+        if net.cond_channels is not None or net.num_labels is not None:
+            raise NotImplementedError("guidance through a conditional UNetPredictor is not implemented")
+        if net.out_channels % 16:
+            raise ValueError("the predictor's out_channels must be a multiple of 16 for the tcgen05 head conv")
+        self.net, self.batch, self.t, self.rate, self.out_conv = net, batch, t, rate, out_conv
+        self.device = next(net.parameters()).device
+        fwd = engine.build_predictor_plan(net, batch, t, None, backend, keep_activations=True)
+        self.fwd = fwd
+        lib = L.load()
+        head_gn, head_conv = net.out[0][0], net.out[1]
+        bwd = engine.Plan(self.device, batch, backend)
+        w = fwd.weights
+        bk = Backward(bwd, batch, fwd.saved, fwd.ab, w.film_offsets, w.film_total, extra_elems=max(net.out_channels, net.base_channels) * t)
+        self.features = fwd.eps                      # [batch, out_channels, t]
+        self.d_features = bwd.empty(batch, net.out_channels, t)
+        self.dx = bwd.empty(batch, 1, t)
+        if out_conv is not None:                     # logits = out_conv(features[:, :, ::rate])
+            t1 = t // rate
+            self.sampled = torch.empty(batch, net.out_channels, t1, device=self.device)
+            self.logits = torch.empty(batch, out_conv.out_channels, t1, device=self.device)
+            self.d_logits = bwd.empty(batch, out_conv.out_channels, t1)
+            self.d_sampled = bwd.empty(batch, net.out_channels, t1)
+            self.packed_out = engine.pack_weights(out_conv.weight, None, L.PREC_BF16X3)
+            if self.packed_out is None:
+                raise ValueError("EncoderPredictor: num_latents and bottleneck_dim must be multiples of 16")
+            bk.conv_t(self.d_logits.data_ptr(), out_conv.out_channels, net.out_channels, t1, 1, 1, out_conv.weight, self.d_sampled.data_ptr())
+            self._scatter_in_backward = True
+        else:
+            self.d_logits = self.d_features
+            self._scatter_in_backward = False
+        # head conv^T: d(gelu(GN(h_last))) = conv^T(d_features); then the GroupNorm in front of it
+        d_act = bwd.empty(batch, net.base_channels, t)
+        self._head_conv_t_at = len(bwd.descs)
+        bk.conv_t(self.d_features.data_ptr(), net.out_channels, net.base_channels, t, 3, 1, head_conv.weight, d_act.data_ptr())
+        fin_head = engine._emit_gn(bwd, [fwd.h_last], head_gn, bk.prep, bk.prep, standalone=False)
+        bk.gn_backward(fin_head, d_act.data_ptr(), [fwd.h_last], 0, [bwd.empty(batch, fwd.h_last.c, fwd.h_last.t)])
+        for blk, srcs, u, out, mode in reversed(fwd.saved):
+            bk.block(blk, srcs, u, out, mode)
+        cb = L.ConvInBwd()
+        cb.batch, cb.c, cb.t = batch, net.base_channels, t
+        cb.dh, cb.w, cb.dx = bk.grad_of(fwd.h0).data_ptr(), L.ptr(net.in_conv.weight), self.dx.data_ptr()
+        bwd.add(L.OP_CONV_IN_BWD, cb)
+        self.bk = bk
+        self.bwd = bwd.compile()
+        self._lib = lib
+
+    def forward(self, x: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
+        plan, net = self.fwd, self.net
+        engine.stage_predictor_inputs(net, plan, x, ts, None, None)
+        plan.run()
+        self.generation += 1
+        if self.out_conv is None:
+            return self.features.clone()
+        stream = L.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.vqvs_stride_sample(self.features.data_ptr(), self.sampled.data_ptr(), self.batch * net.out_channels,
+                                                 self.t, self.rate, 0, stream), "vqvs_stride_sample")
+            d = L.Conv()
+            d.batch, d.c_a, d.t_in, d.c_out, d.t_out = self.batch, net.out_channels, self.t // self.rate, self.out_conv.out_channels, self.t // self.rate
+            d.ksize, d.dilation = 1, 1
+            d.xa, d.out, d.bias = self.sampled.data_ptr(), self.logits.data_ptr(), L.ptr(self.out_conv.bias)
+            d.w_packed = self.packed_out.img.data_ptr()
+            d.reserved_ = self.packed_out.prec << L.CONV_PREC_SHIFT
+            L.check(self._lib.vqvs_conv1d_umma(C.byref(d), stream), "vqvs_conv1d_umma")
+        return self.logits.clone()
+
+    def backward(self, d_out: torch.Tensor, generation: int) -> torch.Tensor:
+        self._check_generation(generation)
+        self.d_logits.copy_(d_out.to(self.d_logits), non_blocking=True)
+        if self._scatter_in_backward:
+            # the program's first two ops are the acc memset and out_conv^T; the strided scatter sits between out_conv^T and
+            # the head conv^T, so the program runs in two pieces around it
+            n0 = self._head_conv_t_at
+            stream = L.stream_ptr(self.device)
+            with torch.cuda.device(self.device):
+                L.check(self._lib.vqvs_run(self.bwd.ops, n0, stream), "vqvs_run")
+                L.check(self._lib.vqvs_stride_sample(self.d_sampled.data_ptr(), self.d_features.data_ptr(),
+                                                     self.batch * self.net.out_channels, self.t, self.rate, 1, stream), "vqvs_stride_sample")
+                rest = C.cast(C.byref(self.bwd.ops, n0 * C.sizeof(L.Op)), C.POINTER(L.Op))
+                L.check(self._lib.vqvs_run(rest, len(self.bwd.descs) - n0, stream), "vqvs_run")
+        else:
+            self.bwd.run()
+        return self.dx.clone()
+
+
+def classifier_plans(clf, x: torch.Tensor) -> GuidancePlans:
     engine._require_cuda(x)
     engine._check_input(x, 1)
     backend = engine.backend_default()
@@ -261,7 +412,7 @@ class ClassifierFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ts, clf):
-        plans = plans_for(clf, x)
+        plans = classifier_plans(clf, x)
         logits = plans.forward(x, ts)
         ctx.plans, ctx.generation, ctx.x_dtype = plans, plans.generation, x.dtype
         return logits
@@ -273,9 +424,24 @@ class ClassifierFunction(torch.autograd.Function):
         return dx.to(ctx.x_dtype), None, None
 
 
-def attention_heads(channels: int, head_channels: int) -> int:
-    return channels // head_channels
+class PredictorFunction(torch.autograd.Function):
+    """EncoderPredictor.forward: logits [N x D x T/R] with a native backward to x."""
 
+    @staticmethod
+    def forward(ctx, x, ts, owner):
+        engine._require_cuda(x, ts)
+        engine._check_input(x, 1)
+        backend = engine.backend_default()
+        batch, _, t = x.shape
+        key = (batch, t, x.device.index, backend)
+        plans = owner._plans.get(key, engine._signature(owner), lambda: PredictorGuidancePlans(
+            owner.unet, batch, t, backend, rate=owner.downsample_rate, out_conv=owner.out))
+        out = plans.forward(x, ts)
+        ctx.plans, ctx.generation, ctx.x_dtype = plans, plans.generation, x.dtype
+        return out
 
-def _unused(*a):  # keep linters quiet about typing-only imports
-    return List, math
+    @staticmethod
+    def backward(ctx, d_out):
+        with torch.no_grad():
+            dx = ctx.plans.backward(d_out.contiguous(), ctx.generation)
+        return dx.to(ctx.x_dtype), None, None

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VQVS_LIB") or os.path.join(_HERE, "libvqvs.so")
 
 # --- constants (keep in sync with include/vqvs.h) ----------------------------
-ABI_VERSION = 5
+ABI_VERSION = 6
 RESIZE_NONE, RESIZE_DOWN2, RESIZE_UP2 = 0, 1, 2
 SKIP_NONE, SKIP_IDENTITY, SKIP_CONV1X1 = 0, 1, 2
 OUT_EPS, OUT_PREV, OUT_X0_SUM = 0, 1, 2
@@ -86,7 +86,7 @@ class GnBwdPrep(C.Structure):
 
 
 class GeluBwd(C.Structure):
-    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("up", _i32),
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("up", _i32), ("c_total", _i32), ("c_off", _i32),
                 ("d_in", _p), ("z", _p), ("prep", _p), ("q", _p), ("acc", _p)]
 
 
@@ -96,8 +96,8 @@ class GnBwdFinalize(C.Structure):
 
 
 class Affine3(C.Structure):
-    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("add_mode", _i32),
-                ("q", _p), ("z", _p), ("coef", _p), ("add", _p), ("out", _p)]
+    _fields_ = [("batch", _i32), ("c", _i32), ("t", _i32), ("add_mode", _i32), ("c_total", _i32), ("c_off", _i32),
+                ("q", _p), ("z", _p), ("coef", _p), ("add", _p), ("add2", _p), ("out", _p)]
 
 
 class ConvInBwd(C.Structure):
@@ -154,6 +154,7 @@ SIGNATURES = {
     "vqvs_gn_bwd_finalize": (C.c_int, [C.POINTER(GnBwdFinalize), _p]),
     "vqvs_affine3": (C.c_int, [C.POINTER(Affine3), _p]),
     "vqvs_conv_in_bwd": (C.c_int, [C.POINTER(ConvInBwd), _p]),
+    "vqvs_stride_sample": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "vqvs_attnpool_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vqvs_attnpool_fwd": (C.c_int, [C.POINTER(AttnPool), _p]),
     "vqvs_attnpool_bwd": (C.c_int, [C.POINTER(AttnPool), _p]),
