@@ -62,6 +62,7 @@ struct Geo {
   int pad, rows;            // halo and operand rows (= 128 + 2*pad)
   int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
   int epi_fast, epi_nch, epi_na;  // register-statistics epilogue: eligible / 32-column chunks per warp / accumulators per chunk
+  int epi_w16;                    // 32-channel N tile: the two warps of a TMEM lane quarter take 16 columns each (per-channel statistics)
   int prec;                 // operand format: VQVS_PREC_BF16X3 (hi/lo split, three products) or VQVS_PREC_F16 (one fp16 product)
   int stack;                // 1: weight rows are [W_hi ; W_lo] (N = 2*n_tile): two MMAs per tap give all four
                             //    hi/lo products, the epilogue adds the two column halves
@@ -1303,10 +1304,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     // (eligibility and the accumulator plan are decided on the host: epilogue_plan())
     const int nch = g.epi_nch, na = g.epi_na;
     const bool fast = LEAN || g.epi_fast;
-    auto run_fast = [&](auto nch_c, auto na_c, auto skipk_c) {
+    auto run_fast = [&](auto nch_c, auto na_c, auto skipk_c, auto w16_c) {
       constexpr int NCH = decltype(nch_c)::value;
       constexpr int NA = decltype(na_c)::value;        // statistics accumulators per 32-column chunk (granularity 32 / NA)
-      constexpr int GSH = NA == 16 ? 1 : NA == 8 ? 2 : 3;  // log2 of the granularity
+      // W16: a 32-channel N tile (the level-0/1 layers of base_channels = 32 models: unet32, the guidance classifier).  Each
+      // warp owns 16 columns (two 8-column pieces) and keeps PER-CHANNEL statistics (32 channels / 32 groups = 1 per group).
+      constexpr bool W16 = decltype(w16_c)::value;
+      constexpr int NSUB = W16 ? 2 : 4;                // 8-column pieces per chunk
+      constexpr int GSH = W16 ? 0 : NA == 16 ? 1 : NA == 8 ? 2 : 3;  // log2 of the granularity
       constexpr int SKIPK = decltype(skipk_c)::value;  // 0: no identity skip, 1: identity (none / nearest x2), 2: identity, pooled
       constexpr int STAT_FLUSH_TILES = 32;
       float s1[NCH][NA], s2[NCH][NA];
@@ -1329,7 +1334,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           }
           const float r = column_sums32(arr, lane);  // lane l: l < NA -> sum of granule l, l < 2 NA -> sumsq of granule l - NA
           const int gi = lane < NA ? lane : lane - NA;
-          const int co = fnt * g.n_tile + (half + EPI_SPLIT * c) * 32 + (gi << GSH);
+          const int co = fnt * g.n_tile + (W16 ? half * 16 : (half + EPI_SPLIT * c) * 32) + (gi << GSH);
           if (lane < 2 * NA && !(dbg_flags & 2))
             atomicAdd(d.stats_out + ((size_t)fn * d.c_out + co) * 2 + (lane < NA ? 0 : 1), (double)r);
         }
@@ -1364,7 +1369,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const int tn = t0 + MT * TILE_M + quarter * 32;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            const int co = nt * g.n_tile + (half + EPI_SPLIT * c) * 32 + lane;
+            const int co = nt * g.n_tile + (W16 ? half * 16 + (lane & 15) : (half + EPI_SPLIT * c) * 32 + lane);
             const float* sp = co < d.s_a ? d.sa + ((size_t)n * d.s_a + co) * d.t_skip
                                          : d.sb + ((size_t)n * d.s_b + (co - d.s_a)) * d.t_skip;
 #pragma unroll
@@ -1387,7 +1392,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           const bool t_ok = t < d.t_out;
           // Output and identity-skip pointers WALK the tile (8 channels per piece, one 64-bit multiply-add per access): a full
           // index computation per piece cost ~12 integer instructions of the ~66 a piece takes (ncu, profiles/r2_*).
-          float* op = d.out + ((size_t)n * d.c_out + nt * g.n_tile + half * 32) * d.t_out + t;
+          float* op = d.out + ((size_t)n * d.c_out + nt * g.n_tile + half * (W16 ? 16 : 32)) * d.t_out + t;
           const int ts_out = d.t_out, ts_skip = d.t_skip;
           const float* skp = nullptr;
           auto skip_chunk = [&](int c0_) {  // first piece of a 32-channel chunk (chunks never straddle the two concat sources)
@@ -1419,14 +1424,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           // the first piece's operands are requested BEFORE waiting for the accumulator, each later piece's while
           // the previous piece is being stored (the next item's lines were already prefetched into L2 above)
           if (SKIPK != 0 && t_ok) {
-            skip_chunk(half * 32);
+            skip_chunk(half * (W16 ? 16 : 32));
             load_skip(sk);
           }
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-              const int c0 = (half + EPI_SPLIT * c) * 32 + sub * 8;  // first column of this 8-wide piece
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const int c0 = (W16 ? half * 16 : (half + EPI_SPLIT * c) * 32) + sub * 8;  // first column of this 8-wide piece
               if (!waited) {
                 PROF_ADD(1, tprev);
                 mbar_wait(ACC_FULL(buf), acc_par);
@@ -1437,14 +1442,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
               uint32_t vr[8], wr[8];
               tmem_ld8_nowait(acc_addr + c0, vr);
               if (stack) tmem_ld8_nowait(acc_addr + g.n_tile + c0, wr);
-              constexpr int kLast = 4 * NCH - 1;
-              const bool has_next = c * 4 + sub < kLast;
+              constexpr int kLast = NSUB * NCH - 1;
+              const bool has_next = c * NSUB + sub < kLast;
               if (SKIPK != 0 && t_ok && has_next) {
-                if (sub == 3) skip_chunk((half + EPI_SPLIT * (c + 1)) * 32);
+                if (sub == NSUB - 1) skip_chunk((half + EPI_SPLIT * (c + 1)) * 32);
                 load_skip(skn);
               }
               tmem_ld_wait();
-              if (j == MT - 1 && c == NCH - 1 && sub == 3) {  // last TMEM read of the item: hand the accumulators back
+              if (j == MT - 1 && c == NCH - 1 && sub == NSUB - 1) {  // last TMEM read of the item: hand the accumulators back
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(buf));
               }
@@ -1475,7 +1480,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   }
                 }
               }
-              op += (sub == 3 ? 8 + 32 * (EPI_SPLIT - 1) : 8) * (ptrdiff_t)ts_out;  // next piece (next chunk of this warp after 4)
+              op += (sub == NSUB - 1 && !W16 ? 8 + 32 * (EPI_SPLIT - 1) : 8) * (ptrdiff_t)ts_out;  // next piece (next chunk of this warp after 4)
               if (SKIPK != 0 && has_next) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sk[i] = skn[i];
@@ -1488,21 +1493,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     };
     if (fast) {
       const int skipk = d.skip_mode != VQVS_SKIP_IDENTITY ? 0 : d.skip_resize == VQVS_RESIZE_DOWN2 ? 2 : 1;
-      auto dispatch_skip = [&](auto nch_c, auto na_c) {
-        if (skipk == 0) run_fast(nch_c, na_c, std::integral_constant<int, 0>{});
-        else if (skipk == 1) run_fast(nch_c, na_c, std::integral_constant<int, 1>{});
-        else run_fast(nch_c, na_c, std::integral_constant<int, 2>{});
+      auto dispatch_skip = [&](auto nch_c, auto na_c, auto w16_c) {
+        if (skipk == 0) run_fast(nch_c, na_c, std::integral_constant<int, 0>{}, w16_c);
+        else if (skipk == 1) run_fast(nch_c, na_c, std::integral_constant<int, 1>{}, w16_c);
+        else run_fast(nch_c, na_c, std::integral_constant<int, 2>{}, w16_c);
       };
       using I1 = std::integral_constant<int, 1>;
       using I2 = std::integral_constant<int, 2>;
       using I4 = std::integral_constant<int, 4>;
       using I8 = std::integral_constant<int, 8>;
       using I16 = std::integral_constant<int, 16>;
-      if (nch == 1) dispatch_skip(I1{}, I16{});
-      else if (nch == 2 && na == 16) dispatch_skip(I2{}, I16{});
-      else if (nch == 2) dispatch_skip(I2{}, I8{});
-      else if (na == 8) dispatch_skip(I4{}, I8{});
-      else dispatch_skip(I4{}, I4{});
+      if (g.epi_w16) dispatch_skip(I1{}, I16{}, std::true_type{});
+      else if (nch == 1) dispatch_skip(I1{}, I16{}, std::false_type{});
+      else if (nch == 2 && na == 16) dispatch_skip(I2{}, I16{}, std::false_type{});
+      else if (nch == 2) dispatch_skip(I2{}, I8{}, std::false_type{});
+      else if (na == 8) dispatch_skip(I4{}, I8{}, std::false_type{});
+      else dispatch_skip(I4{}, I4{}, std::false_type{});
     } else if constexpr (!LEAN) {
     auto flush_stats = [&](int fn, int fnt) {
 #pragma unroll
@@ -2107,11 +2113,19 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     // as few accumulators as the granularity allows, at most 32 registers per kind in total
     const int na = !stats ? 4 : nch == 1 ? 16 : nch == 2 ? (gran_log2 >= 2 ? 8 : 16) : (gran_log2 >= 3 ? 4 : 8);
     const bool gran_ok = !stats || (gran_log2 >= 1 && (32 >> gran_log2) <= na);
+    g.epi_w16 = 0;
+    if (g.n_tile == 32 && g.n_tiles == 1) {  // 32 output channels: 16 columns per warp, per-channel statistics in 16 accumulators
+      g.epi_nch = 1;
+      g.epi_na = 16;
+      g.epi_w16 = 1;
+      g.epi_fast = !(d->reserved_ & 32);
+    } else {
     g.epi_nch = nch;
     g.epi_na = na;
     g.epi_fast = gran_ok && !(g.n_tile & 31) && (nch == 1 || nch == 2 || nch == 4) && n_chunks32 == nch * umma::EPI_SPLIT &&
                  !(d->reserved_ & 32) &&
                  !(d->skip_mode == VQVS_SKIP_IDENTITY && d->s_b && (d->s_a & 31));  // skip chunks of 32 channels stay in one source
+    }
   }
   const bool lean = g.tma && g.epi_fast && !(d->reserved_ & 0x3FF);  // any profiling / ablation bit selects the generic kernel
   // (PLAIN kinds compile the staging pitches in: 136 floats for the main taps at dilation 1 or 2, 128 for the 1x1 skip)
