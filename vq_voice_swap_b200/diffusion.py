@@ -135,6 +135,25 @@ class Diffusion:
             return self._update(x_t, ts, step, eps, engine._f32(noise), co, constrain, cond_fn).to(dtype)
 
     # -- sampler ----------------------------------------------------------------------------
+    def _step_tables(self, x_T, steps: int, sigma_large: bool, schedule: Optional[Callable]):
+        """Every step's timestep and update coefficients, evaluated ONCE on the host (all rows of a batch share t, reference
+        diffusion.py:115) with the same fp32 torch ops the reference runs per step on the device, then moved in one copy:
+        the sampling loop itself launches no ATen kernel besides the noise draw."""
+        n = x_T.shape[0]
+        grid = torch.tensor([(i + 1) / steps for i in range(steps)][::-1], dtype=torch.float32)
+        ts, t_step = grid, torch.full_like(grid, 1 / steps)
+        if schedule is not None:  # sample-time remap (:116-118), applied elementwise like the reference does per step
+            t_step = schedule(grid) - schedule(grid - 1 / steps)
+            ts = schedule(grid)
+        co = self.step_coefficients(ts, t_step, sigma_large)
+        dev = x_T.device
+        return dict(
+            ts=ts.to(dev)[:, None].expand(steps, n).contiguous(),
+            t_step=t_step.to(dev)[:, None].expand(steps, n).contiguous(),
+            packed=co["packed"].to(dev)[:, None, :].expand(steps, n, 8).contiguous(),
+            **{k: co[k].to(dev)[:, None].expand(steps, n).contiguous() for k in ("alpha", "beta", "sig2", "ab_t")},
+        )
+
     def ddpm_sample(self, x_T, predictor, steps: int, progress: bool = False, sigma_large: bool = False,
                     constrain: bool = False, cond_fn: Callable = None, schedule: Callable = None,
                     noise_fn: Optional[Callable] = None):
@@ -149,9 +168,9 @@ class Diffusion:
             raise RuntimeError("dropout > 0 in train mode is not implemented on the sm_100a path: call model.eval()")
         x_t = engine._f32(x_T)
         bufs = [torch.empty_like(x_t), torch.empty_like(x_t)]
-        grid = [(i + 1) / steps for i in range(steps)]
-        t_step = 1 / steps
-        its = enumerate(grid[::-1])
+        with torch.no_grad():
+            tab = self._step_tables(x_t, steps, sigma_large, schedule)
+        its = range(steps)
         if progress:
             from tqdm.auto import tqdm
 
@@ -162,13 +181,10 @@ class Diffusion:
                 return None  # zeros on the last step (:127)
             return torch.randn_like(x_t) if noise_fn is None else engine._f32(noise_fn(i, x_t))
 
-        for i, t in its:
-            ts = torch.tensor([t] * x_T.shape[0]).to(x_t)
-            if schedule is not None:
-                t_step = schedule(ts) - schedule(ts - 1 / steps)
-                ts = schedule(ts)
+        for i in its:
+            ts, t_step = tab["ts"][i], tab["t_step"][i]
+            co = {k: tab[k][i] for k in ("packed", "alpha", "beta", "sig2", "ab_t")}
             with torch.no_grad():
-                co = self.step_coefficients(ts, t_step, sigma_large)
                 out = bufs[i & 1]
                 if fast is not None:
                     # our predictor consumes no random numbers, so drawing the noise first keeps the generator sequence of
