@@ -8,7 +8,7 @@ from vq_voice_swap_b200.unet import ResBlock
 
 FLAGS = [int(x) for x in os.environ.get("ABLATE", "0,1,8,16,64,80,4").split(",")]
 PROF = os.environ.get("PROF", "0") == "1"
-NAMES = ["xf.wait_ab", "xf.wait_raw", "xf.work", "xf.loop", "tma.0", "tma.1", "tma.2", "tma.3", "mma.wait_ab", "mma.issue",
+NAMES = ["xf.wait_ab", "xf.wait_raw", "xf.work", "xf.loop", "mma.wait_b", "cta.total", "cta.prologue", "tma.3", "mma.wait_ab", "mma.issue",
          "mma.wait_acc", "mma.loop", "epi.wait_full", "epi.stats+next", "epi.tmem_ld", "epi.store"]
 lib = L.load()
 for spec in sys.argv[1:]:
@@ -27,7 +27,7 @@ for spec in sys.argv[1:]:
         one = (L.Op * 1)(); one[0].kind = kind; one[0].desc = C.addressof(d)
         alg = 4.0 * d.batch * ((d.c_a + d.c_b) * d.t_in + d.c_out * d.t_out + ((d.s_a + d.s_b) * d.t_skip if d.skip_mode else 0))
         line = []; prof = ''
-        keep = d.reserved_ & 1024  # VQVS_CONV_PAIR_STATS set by the engine
+        keep = d.reserved_ & ~0x3FF  # VQVS_CONV_PAIR_STATS, statistics granularity and operand format set by the engine
         for fl in FLAGS:
             d.reserved_ = fl | keep | (512 if PROF else 0)
             ms = 0.0; buf = (C.c_float * 1)()

@@ -219,7 +219,7 @@ def conv_precision(c_out: int, base_channels: Optional[int]) -> int:
     forced = os.environ.get("VQVS_PREC")
     if forced:
         return {"bf16x3": L.PREC_BF16X3, "f16": L.PREC_F16}[forced]
-    if base_channels is not None and c_out >= 4 * base_channels:
+    if base_channels is not None and c_out >= int(os.environ.get("VQVS_F16_FROM", "4")) * base_channels:
         return L.PREC_F16
     return L.PREC_BF16X3
 
@@ -263,7 +263,7 @@ def weights_for(net, blocks: Sequence, backend: str, reduced_precision: bool = F
     keeps bf16x3 everywhere because its outputs decide code indices)."""
     sig = _signature(net)
     w = getattr(net, "_vqvs_weights", None)
-    key = (sig, backend, reduced_precision, os.environ.get("VQVS_PREC"))
+    key = (sig, backend, reduced_precision, os.environ.get("VQVS_PREC"), os.environ.get("VQVS_F16_FROM"))
     if w is not None and w.signature == key:
         return w
     w = Weights()
