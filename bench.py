@@ -188,6 +188,17 @@ def profile_kernels(model, x, reps=3, cond=None, labels=None):
     return plan, acc, by_kind, umma
 
 
+PRECISION_FROM = {"default": None, "fast128": "2", "fast": "1"}  # VQVS_F16_FROM: fp16 single products from this multiple of bc
+PRECISION_DTYPE = {
+    "default": "fp32 storage and accumulation; tensor-core products bf16x3 (hi/lo split), one fp16 product for C_out >= 4*bc and for "
+               "2*bc blocks at <= 1/16 of the input length (unet64 forward 8.9e-5, 50-step sample 2.0e-5 vs the fp32 oracle)",
+    "fast128": "fp32 storage and accumulation; tensor-core products bf16x3 for C_out < 2*bc, one fp16 product from 2*bc "
+               "(NOT the headline: unet64 forward 3.7e-4 vs the fp32 oracle)",
+    "fast": "fp32 storage and accumulation; one fp16 tensor-core product per tap everywhere (NOT the headline: TF32-class, "
+            "unet64 forward 1.0e-3, 50-step sample 2.8e-4 vs the fp32 oracle)",
+}
+
+
 def traffic_from_profiles():
     """Launch-weighted dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
     for name in ("r2_dram_traffic.json", "ncu_summary.json"):
@@ -338,9 +349,10 @@ def run_ours(args):
         "metric": cfg["metric"], "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "fp32 storage and accumulation; tensor-core products bf16x3 (hi/lo split), one fp16 product for C_out >= 4*bc",
+        "dtype": PRECISION_DTYPE[args.precision],
         "data": "synthetic",
         "config": {"workload": cfg["workload"].format(bc=cfg["bc"], b=B, s=dsteps), "global_batch": world * B,
+                   "precision": args.precision,
                    "l2": "activations (>= 0.5 GB per tensor) exceed the 126 MB L2; no flush needed",
                    "weights": "random-init architecture, zero-init tensors re-randomised (seeded)",
                    "noise": "device Philox keyed by (seed, global sample index, step): N-GPU output == 1-GPU output",
@@ -570,7 +582,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the informational torch-eager-on-GPU comparator")
     ap.add_argument("--force-port", action="store_true", help="CPU arm: time the oracle port even if baseline/_ref exists")
+    ap.add_argument("--precision", default="default", choices=["default", "fast128", "fast"],
+                    help="operand-format policy of the predictor convs (engine.conv_precision): default = bf16x3, fp16 for "
+                         "C_out >= 4*bc (unet64 forward 4.9e-5 vs the fp32 oracle); fast128 = fp16 from 2*bc (3.7e-4); fast = one fp16 "
+                         "product everywhere (1.0e-3 per forward, 2.8e-4 on a 50-step sample: the TF32 class of the reference's own "
+                         "GPU path).  Only the default is the headline configuration.")
     args = ap.parse_args()
+    if PRECISION_FROM[args.precision]:
+        os.environ["VQVS_F16_FROM"] = PRECISION_FROM[args.precision]
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:  # convenience: self-launch one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517")] + sys.argv

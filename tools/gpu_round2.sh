@@ -13,6 +13,9 @@ timeout -s KILL 600 python bench.py --impl reference --steps 2 --warmup 1 > $out
 for c in vqvae guided; do
   timeout -s KILL 900 python bench.py --config $c --steps 2 --warmup 2 --no-eager --no-cpu-baseline > $out/bench_$c.json 2> $out/bench_$c.err; cut -c1-160 $out/bench_$c.json
 done
+for pr in fast128 fast; do
+  timeout -s KILL 600 python bench.py --precision $pr --steps 2 --warmup 3 --no-eager --no-cpu-baseline > $out/bench_uncond_$pr.json 2> $out/bench_$pr.err; cut -c1-120 $out/bench_uncond_$pr.json
+done
 for b in 1 4; do
   timeout -s KILL 600 python bench.py --batch $b --steps 3 --warmup 2 --no-eager --no-cpu-baseline > $out/bench_uncond_b$b.json 2> $out/bench_b$b.err
 done

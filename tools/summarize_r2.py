@@ -7,6 +7,7 @@ R = sys.argv[1]
 P = "profiles"
 for src, dst in [("bench_uncond.json", "r2_bench_n1.json"), ("bench_reference.json", "r2_bench_reference_n1.json"),
                  ("bench_vqvae.json", "r2_bench_vqvae_n1.json"), ("bench_guided.json", "r2_bench_guided_n1.json"),
+                 ("bench_uncond_fast128.json", "r2_bench_uncond_fast128_n1.json"), ("bench_uncond_fast.json", "r2_bench_uncond_fast_n1.json"),
                  ("bench_uncond_b1.json", "r2_bench_uncond_batch1.json"), ("bench_uncond_b4.json", "r2_bench_uncond_batch4.json"),
                  ("op_profile.txt", "r2_op_profile.txt"), ("op_profile_unet32_b32.txt", "r2_op_profile_unet32_b32.txt"),
                  ("gpu.txt", "r2_gpu.txt"), ("pytest_gpu.txt", "r2_pytest_gpu.txt"), ("smoke.txt", "r2_smoke.txt"),

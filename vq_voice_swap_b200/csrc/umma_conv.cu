@@ -114,7 +114,8 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   // Narrow layers: an MMA costs the same ~77 cycles for N = 64 and N = 128 (tools/mma_bench.cu), so stacking
   // W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs,
   // which also adds the lo*lo term).
-  g->stack = (parts == 2 && (g->n_tile == 32 || g->n_tile == 64)) ? 1 : 0;
+  static const bool no_stack = getenv("VQVS_NO_STACK") != nullptr;  // tuning aid: three separate products for narrow tiles too
+  g->stack = (parts == 2 && (g->n_tile == 32 || g->n_tile == 64) && !no_stack) ? 1 : 0;
   int cols = 32;
   while (cols < (g->stack ? 2 : 1) * g->n_tile) cols *= 2;
   g->acc_cols = cols;

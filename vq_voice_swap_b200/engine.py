@@ -209,17 +209,24 @@ class Packed:
         self.img, self.prec = img, prec
 
 
-def conv_precision(c_out: int, base_channels: Optional[int]) -> int:
+def conv_precision(c_out: int, base_channels: Optional[int], rel_length: float = 1.0) -> int:
     """Operand format of a predictor conv (include/vqvs.h VQVS_PREC_*).
 
-    The deep levels (C_out >= 4 * base_channels: 256 and 512 channels in unet64, a quarter of the step and bound by the
-    tensor pipe under bf16x3) run ONE fp16 product per tap; everything else keeps the bf16 hi/lo split.  Measured: a whole
-    UNet forward with this rule differs from the fp32 oracle by 6e-5 (tools/precision_study.py; bf16x3 everywhere: 1.5e-5)
-    against the 1e-3 the north star allows.  VQVS_PREC=bf16x3 | f16 forces one format everywhere (study / tests)."""
+    One fp16 product per tap where it is cheap in error: the deep levels (C_out >= 4 * base_channels: 256 and 512 channels in
+    unet64, bound by the tensor pipe under bf16x3) and the 2 * base_channels blocks whose output is at most 1/16 of the input
+    length (128 channels at T = 4000 in unet64); everything else keeps the bf16 hi/lo split.  Measured on the B200
+    (tools/precision_policy_study.py, unet64 forward at T = 64000 against the fp32 oracle): 1.2e-5 with bf16x3 everywhere,
+    4.9e-5 with the first rule, 8.9e-5 with both -- the budget is 2e-4, a fifth of the 1e-3 the north star allows.  Wider
+    choices are opt-in: VQVS_F16_FROM=2 (all 2 * bc blocks: 3.7e-4) and =1 (everything: 1.0e-3 per forward, 2.8e-4 on a
+    50-step sample -- the TF32 class of the reference's own GPU path); VQVS_PREC=bf16x3 | f16 forces one format everywhere."""
     forced = os.environ.get("VQVS_PREC")
     if forced:
         return {"bf16x3": L.PREC_BF16X3, "f16": L.PREC_F16}[forced]
-    if base_channels is not None and c_out >= int(os.environ.get("VQVS_F16_FROM", "4")) * base_channels:
+    if base_channels is None:
+        return L.PREC_BF16X3
+    if c_out >= int(os.environ.get("VQVS_F16_FROM", "4")) * base_channels:
+        return L.PREC_F16
+    if c_out >= 2 * base_channels and rel_length <= 1.0 / 16 and os.environ.get("VQVS_F16_SHORT", "1") == "1":
         return L.PREC_F16
     return L.PREC_BF16X3
 
@@ -263,7 +270,7 @@ def weights_for(net, blocks: Sequence, backend: str, reduced_precision: bool = F
     keeps bf16x3 everywhere because its outputs decide code indices)."""
     sig = _signature(net)
     w = getattr(net, "_vqvs_weights", None)
-    key = (sig, backend, reduced_precision, os.environ.get("VQVS_PREC"), os.environ.get("VQVS_F16_FROM"))
+    key = (sig, backend, reduced_precision) + tuple(os.environ.get(k) for k in ("VQVS_PREC", "VQVS_F16_FROM", "VQVS_BF16X3_FIRST", "VQVS_BF16X3_LAST", "VQVS_F16_BLOCKS", "VQVS_F16_SHORT"))
     if w is not None and w.signature == key:
         return w
     w = Weights()
@@ -272,8 +279,20 @@ def weights_for(net, blocks: Sequence, backend: str, reduced_precision: bool = F
     bc = getattr(net, "base_channels", None) if reduced_precision else None
     with torch.no_grad():
         if backend == "umma":
-            for blk in blocks:
-                prec = conv_precision(blk.out_channels, bc)
+            extra_f16 = set()  # VQVS_F16_BLOCKS="6-14,46-52": block indices (down + middle + up order) forced to fp16 (study knob)
+            for part in filter(None, os.environ.get("VQVS_F16_BLOCKS", "").split(",")):
+                lo, _, hi = part.partition("-")
+                extra_f16.update(range(int(lo), int(hi or lo) + 1))
+            keep_first = int(os.environ.get("VQVS_BF16X3_FIRST", "0"))  # (study knobs: blocks at either end of the network
+            keep_last = int(os.environ.get("VQVS_BF16X3_LAST", "0"))    #  that keep the bf16 hi/lo split whatever the rule says)
+            rel = 1.0  # length of the block's output relative to the network input (both convs of a block run at it)
+            for bi, blk in enumerate(blocks):
+                rel *= float(getattr(blk, "scale_factor", 1.0) or 1.0)
+                prec = conv_precision(blk.out_channels, bc, rel)
+                if bc is not None and (bi < keep_first or bi >= len(blocks) - keep_last) and not os.environ.get("VQVS_PREC"):
+                    prec = L.PREC_BF16X3
+                if bc is not None and bi in extra_f16:
+                    prec = L.PREC_F16
                 w.packed[(id(blk), 1)] = _pack(blk.pre_cond[2], None, prec)
                 w.packed[(id(blk), 2)] = _pack(_tail_conv(blk), _skip_proj(blk), prec)
             for name in ("cond_proj",):
