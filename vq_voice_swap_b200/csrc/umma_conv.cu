@@ -111,11 +111,13 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   g->b_unit_main = ksize * g->n_tile * 32 * parts;
   g->b_unit_skip = g->n_tile * 32 * parts;
   g->per_tile_bytes = (long long)g->nkb_main * g->b_unit_main + (long long)g->nkb_skip * g->b_unit_skip;
-  // Narrow layers: an MMA costs the same ~77 cycles for N = 64 and N = 128 (tools/mma_bench.cu), so stacking
-  // W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs,
-  // which also adds the lo*lo term).
-  static const bool no_stack = getenv("VQVS_NO_STACK") != nullptr;  // tuning aid: three separate products for narrow tiles too
-  g->stack = (parts == 2 && (g->n_tile == 32 || g->n_tile == 64) && !no_stack) ? 1 : 0;
+  // Stacking W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs, which
+  // also adds the lo*lo term).  Kept for 32-channel tiles; 64-channel tiles issue the three products with the A tile of the
+  // second one reused from the collector: same tensor time (51 + 32 + 51 against 2 x 67 clocks), 25 % fewer multiply-adds --
+  // the step runs under the board's power cap, and the freed power came back as +2.9 % SM clock / +2.3 % samples/s
+  // (bench.py A/B on one box) -- and a 64-column accumulator the epilogue reads once.  VQVS_STACK64=1 restores stacking.
+  static const bool stack64 = getenv("VQVS_STACK64") != nullptr;
+  g->stack = (parts == 2 && (g->n_tile == 32 || (g->n_tile == 64 && stack64))) ? 1 : 0;
   int cols = 32;
   while (cols < (g->stack ? 2 : 1) * g->n_tile) cols *= 2;
   g->acc_cols = cols;
@@ -313,11 +315,11 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
   "mov.b64 da, {" A ", %1};\n\tmov.b64 db, {" B ", %2};\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " P ";\n\t"
 // A-operand collector hints (SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE): a product that shares its A tile with the NEXT
 // one keeps it in the tensor core's collector buffer ("fill"), the next one consumes it without fetching it from shared
-// memory again ("lastuse").  hi*hi and hi*lo share A_hi, so one of the three A-tile reads of a tap disappears
-// (8 + 4 + 8 KB instead of 3 x 8 KB of operand traffic for an N = 128 tile) -- shared-memory bandwidth is what the
-// tensor core and the staging warps compete for.  Measured (A/B builds, tools/op_profile.py): no difference on any
-// C_out = 128 layer (+-1 %), so the plain form stays the default; -DVQVS_COLLECTOR enables the hints.
-#ifndef VQVS_COLLECTOR
+// memory again ("lastuse").  hi*hi and hi*lo share A_hi, so one of the three A-tile reads of a tap disappears.  Measured
+// (A/B builds): nothing for N = 128 tiles (those MMAs sit on the 64-clock compute floor either way), but it is what makes
+// three separate products as cheap as two stacked ones for N = 64 (an N = 64 MMA is bound by its operand fetch: 51 clocks,
+// 32 with A reused -- tools/mma_bench.cu), with a quarter fewer multiply-adds.  -DVQVS_NO_COLLECTOR issues plain MMAs.
+#ifdef VQVS_NO_COLLECTOR
 #define VQVS_MMA_FILL_(A, B, P) VQVS_MMA_(A, B, P)
 #define VQVS_MMA_LAST_(A, B, P) VQVS_MMA_(A, B, P)
 #else
@@ -899,7 +901,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   // KIND 3 = PLAIN and additionally no 1x1-skip stages and resident weights (conv1 and identity-skip conv2 of every
   // 64-channel layer: the largest share of a step)
   constexpr bool LEAN = KIND != 0, PLAIN = KIND >= 2, SIMPLE = KIND == 3;
-  constexpr bool STACKED = SIMPLE;  // the host selects KIND 3 only for stacked [W_hi ; W_lo] weight tiles of k = 3 convs
   extern __shared__ __align__(128) uint8_t smem[];
   // mbarriers: raw_full[8] raw_empty[8] b_full[8] b_empty[8] a_full[8] ab_empty[8] acc_full[2] acc_empty[2] w_full
   const uint32_t bar0 = smem_u32(smem);
@@ -1359,7 +1360,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 if (do_mma) mma_group_single1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, b_k);
               }
             } else if (taps == 3) {
-              if (STACKED || g.stack) {
+              if (g.stack) {
                 if (do_mma)
                   mma_group_stack3(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, a_j + tap_rows, a_j + tap_rows + a_lo_off,
                                    a_j + tap2, a_j + tap2 + a_lo_off, b_k, b_k + b_tap_off, b_k + 2 * b_tap_off);
@@ -1370,7 +1371,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                                    b_k + 2 * b_tap_off, b_k + 2 * b_tap_off + b_lo_off);
               }
             } else {
-              if (STACKED || g.stack) {
+              if (g.stack) {
                 if (do_mma) mma_group_stack1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, b_k);
               } else {
                 if (do_mma) mma_group_split1(d_tmem, a_hi32, b_hi32, idesc, accf, a_j, a_j + a_lo_off, b_k, b_k + b_lo_off);
@@ -2263,7 +2264,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
   // (PLAIN kinds compile the staging pitches in: 136 floats for the main taps at dilation 1 or 2, 128 for the 1x1 skip)
   const bool plain = d->resize == VQVS_RESIZE_NONE && (g.nkb_skip == 0 || d->skip_resize == VQVS_RESIZE_NONE) &&
                      g.main_box_w == umma::SIMPLE_BOXW && (g.nkb_skip == 0 || g.skip_box_w == umma::TILE_M);
-  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1 && g.stack && d->ksize == 3;
+  const bool simple = plain && g.nkb_skip == 0 && g.w_resident && g.mt == 1 && g.prec == VQVS_PREC_BF16X3 && g.n_tile <= 64 && d->ksize == 3;
   const int kind = !lean ? 0 : simple ? 3 : plain ? 2 : 1;
   g_last_kind = kind;
   cudaError_t le = kind == 3   ? umma::launch_kind3(g.mt, grid, g.smem_bytes, (cudaStream_t)stream, maps, d, &g, &fin)
