@@ -704,6 +704,7 @@ struct StageView {
   int rows;           // operand rows of this conv (row pitch of the hi/lo blocks)
   int box_w, boxes, x0, tcs, n_rows, t_src, t_conv, resize;
   bool act, f16;
+  bool edge;  // some operand rows of this tile lie outside the sequence (first / last tile of a sample): they must read as zero
 };
 
 // Row-wise work of one thread in one stage: rows row_first, row_first + 32, ... (NIT of them) of ONE 8-channel
@@ -773,27 +774,43 @@ __device__ __forceinline__ void transform_row_group(const StageView& v, const fl
 #pragma unroll
       for (int i = 0; i < 4; ++i) y[r][i] = fma2(y[r][i], bcast2(0.5f), mul2(z[r][i], bcast2(0.5f)));
   }
+  // Out-of-range positions read zero-filled (finite) staging memory, but GELU(shift) != 0: their operand rows must be zero.
+  // Only the first and last tile of a sample have such rows, so the common path stores unconditionally (no per-row range
+  // test, no divergent region) and an edge tile overwrites its out-of-range rows afterwards (same thread, program order).
+  if (v.f16) {  // one fp16 operand row
+    uint4 h[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + 32 * r, tc = v.tcs + row;
-    // out-of-range positions read zero-filled (finite) staging memory; their rows are zeroed after the GELU
-    const bool oob = tc < 0 || tc >= v.t_conv;
-    if (v.f16) {  // one fp16 operand row
-      uint32_t h[4];
+    for (int r = 0; r < R; ++r) {
+      uint32_t q[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float a, b;
         unpack2(y[r][i], a, b);
         const __half2 hb = __floats2half2_rn(a, b);
-        h[i] = oob ? 0u : *reinterpret_cast<const uint32_t*>(&hb);
+        q[i] = *reinterpret_cast<const uint32_t*>(&hb);
       }
-      *reinterpret_cast<uint4*>(a_hi + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-    } else {
-      uint4 hi, lo;
-      split4p(y[r], &hi, &lo);
-      if (oob) hi = lo = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(a_hi + row * 16) = hi;
-      *reinterpret_cast<uint4*>(a_lo + row * 16) = lo;
+      h[r] = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) *reinterpret_cast<uint4*>(a_hi + (row0 + 32 * r) * 16) = h[r];
+  } else {
+    uint4 hi[R], lo[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) split4p(y[r], &hi[r], &lo[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // (all rows packed before the first store: a store's source registers are not recycled under it)
+      *reinterpret_cast<uint4*>(a_hi + (row0 + 32 * r) * 16) = hi[r];
+      *reinterpret_cast<uint4*>(a_lo + (row0 + 32 * r) * 16) = lo[r];
+    }
+  }
+  if (v.edge) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + 32 * r, tc = v.tcs + row;
+      if (tc < 0 || tc >= v.t_conv) {
+        *reinterpret_cast<uint4*>(a_hi + row * 16) = make_uint4(0, 0, 0, 0);
+        if (!v.f16) *reinterpret_cast<uint4*>(a_lo + row * 16) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
 }
@@ -1116,6 +1133,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
           StageView v = is_skip ? vs : vm;
           v.x0 = is_skip ? x0s : x0m;
           v.tcs = is_skip ? t0 : t0 - g.pad;
+          v.edge = v.tcs < 0 || v.tcs + MT * TILE_M + (v.n_rows - TILE_M) > v.t_conv;  // (covers every time tile of the item)
           const int step = is_skip ? skip_step : main_step;
           const float2* ss = s_ss + kb0 * KBLK;
           // Work split of a row-wise stage: the stage has 2*nk chunks of 8 channels; warps 0..7 each own ONE chunk
