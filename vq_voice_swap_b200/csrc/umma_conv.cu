@@ -2088,8 +2088,9 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
     // Re-measured per layer with VQVS_FORCE_MT after the prologue got cheaper (tools/op_profile.py, unet64 batch 64): every
     // bf16x3 layer with a 128-channel N tile is faster with single tiles (3-25 %: finer items, both accumulator sets in
     // flight), while the fp16 layers with a 1x1 skip conv (K up to 3*512 + 1024, the longest weight streams) keep two.
-    if (prec == VQVS_PREC_BF16X3 && g->n_tile <= 128) want1 = true;
-    if (prec == VQVS_PREC_F16 && d->skip_mode == VQVS_SKIP_CONV1X1) want1 = false;
+    static const bool old_rule = getenv("VQVS_MT_RULE_R1") != nullptr;  // (A/B aid: the rounds-based rule alone)
+    if (!old_rule && prec == VQVS_PREC_BF16X3 && g->n_tile <= 128) want1 = true;
+    if (!old_rule && prec == VQVS_PREC_F16 && d->skip_mode == VQVS_SKIP_CONV1X1) want1 = false;
     if (want1) {
       Geo g2 = *g;
       if (!geo(1)) *g = g2;  // keep the two-tile plan if a one-tile plan does not fit
