@@ -36,6 +36,8 @@ names = [n for n in a.only.split(",") if n] or list(CLASSES)
 launch = 0
 for name in names:
     cin, cout, t, scale, dil = CLASSES[name]
+    # a standalone block has no network around it to derive the operand format from: apply the unet64 rule (engine.conv_precision)
+    os.environ["VQVS_PREC"] = "f16" if cout >= 256 else "bf16x3"
     blk = ResBlock(cin, 256, cout, scale_factor=scale, dilation=dil)
     synth.load_synth(blk, "runblock")
     blk = blk.cuda()

@@ -33,7 +33,7 @@ table = {k: {"launches": v[3], "ms_per_unet_step": round(v[0], 3), "share_of_con
              "fp32_equivalent_TFLOPs": round(v[2] / v[0], 1)} for k, v in sorted(cls.items(), key=lambda kv: -kv[1][0])}
 json.dump({"source": "tools/op_profile.py (unet64, batch 64, T = 64000): CUDA events between the launches of one UNet step",
            "conv_ms_per_unet_step": round(tot, 3), "hbm_peak_GBps": peak,
-           "note": "tensor-core work = 3 x fp32-equivalent FLOPs for C_out < 256 (bf16x3), 1 x for C_out >= 256 (fp16)",
+           "note": "tensor-core work = 3 x fp32-equivalent FLOPs for the bf16x3 layers (C_out = 64, and C_out = 128 at T >= 8000), 1 x for the fp16 ones (C_out >= 256, C_out = 128 at T = 4000)",
            "classes": table}, open(f"{P}/r2_class_table.json", "w"), indent=1)
 
 # ---- launch list: duration + DRAM bytes of every launch of one sampler call with one diffusion step ----
