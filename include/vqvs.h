@@ -63,8 +63,9 @@ int vqvs_device_info(int* cc, int* sm_count);
  *
  * x is the channel concatenation [xa ; xb] (torch.cat of unet.py:156 never
  * materialised); scale/shift carry GroupNorm (and FiLM, unet.py:311-314)
- * folded per (sample, channel) by vqvs_gn_finalize.  GELU is the exact erf
- * form (unet.py:341-342).
+ * folded per (sample, channel) by vqvs_gn_finalize.  GELU is the erf form of
+ * unet.py:341-342 (NOT tanh / SiLU), evaluated by approximations with <= 6.4e-7
+ * absolute error (tools/fit_gelu_poly.py; common.cuh gelu_as).
  */
 /* VqvsConv.reserved_ flag: the producer may accumulate statistics per channel PAIR (both channels' sums go to
  * the even channel's slot, the odd slot stays as the caller zeroed it).  Valid when every GroupNorm that
@@ -344,7 +345,7 @@ typedef struct VqvsTimeEmbed {
 } VqvsTimeEmbed;
 int vqvs_time_embed(const VqvsTimeEmbed* d, void* stream);
 
-/* out[i] = GELU(in[i]) (exact erf form); input of cond_layers when a caller supplies emb directly. */
+/* out[i] = GELU(in[i]) (erf form, approximated to <= 4.2e-7 absolute); input of cond_layers when a caller supplies emb directly. */
 int vqvs_gelu(const float* in, float* out, int64_t n, void* stream);
 
 /* All FiLM Linear layers of a network in one launch: ab[n, :] = W_cat * gelu_emb[n] + b_cat,

@@ -31,7 +31,7 @@ void set_error(const char* fmt, ...);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- device helpers -----------------------------------------------------------
-// Exact-erf GELU, reference models/unet.py:341-342 (nn.GELU default).
+// erf-form GELU through libm's erff, reference models/unet.py:341-342 (nn.GELU default).
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -46,7 +46,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Fast exact-erf GELU used by every fused prologue.  GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
+// Fast APPROXIMATION of the erf-form GELU used by the CUDA-core prologues.  GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
 // max |error| 4.2e-7 over [-12, 12] in fp32, tighter than ATen's own fp32 GELU (1.2e-6).
 // Two MUFU ops (rcp, ex2) + 12 FP32 ops per element.
 __device__ __forceinline__ float gelu_as(float x) {

@@ -8,7 +8,7 @@
 // * Weight warp: the operand image pre-split into bf16 hi/lo and pre-arranged by vqvs_pack_conv_weights, resident in
 //   shared memory for the whole CTA when it fits (<= 150 KB), else streamed per K block with cp.async.bulk.
 // * Transform warps (8 + 1 for the halo rows): optional GroupNorm(+FiLM) FINALIZE from the producers' statistics at every
-//   sample change, then per element affine -> exact-erf GELU (packed fp32x2) -> pool / upsample / concat select -> bf16
+//   sample change, then per element affine -> erf-form GELU (packed fp32x2 approximation, <= 6.4e-7) -> pool / upsample / concat select -> bf16
 //   hi + lo split, stored K-major, un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so
 //   the three conv taps are the SAME tile read through descriptors whose start address is shifted by tap*dilation rows --
 //   the halo is staged once.
