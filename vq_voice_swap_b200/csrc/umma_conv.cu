@@ -54,7 +54,6 @@ constexpr int SMEM_GROUP_TABLE = 512;  // byte offset of the 32 x (mean, rstd) f
 constexpr int MAX_RAW_SLOTS = 8;
 constexpr int MAX_B_SLOTS = 8;
 constexpr int MAX_AB_SLOTS = 8;
-constexpr int EPI_STAGE_BYTES = 4096;  // per epilogue warp: two halves of [16 channels][32 positions] fp32
 constexpr int SIMPLE_BOXW = 136;  // staging pitch of every un-resampled conv with dilation 1 or 2 (128 + 2 * 4)
 
 // Host-computed geometry shared by the packer and the kernel.
@@ -65,7 +64,6 @@ struct Geo {
   int acc_cols, tmem_cols;  // TMEM columns of one accumulator / allocated (two accumulators)
   int epi_fast, epi_nch, epi_na;  // register-statistics epilogue: eligible / 32-column chunks per warp / accumulators per chunk
   int epi_w16;                    // 32-channel N tile: the two warps of a TMEM lane quarter take 16 columns each (per-channel statistics)
-  int epi_tma, off_epi;           // 1: the fast epilogue stages 16-channel x 32-position boxes in smem (two 2 KB halves per warp at off_epi) and stores them by TMA
   int prec;                 // operand format: VQVS_PREC_BF16X3 (hi/lo split, three products) or VQVS_PREC_F16 (one fp16 product)
   int stack;                // 1: weight rows are [W_hi ; W_lo] (N = 2*n_tile): two MMAs per tap give all four
                             //    hi/lo products, the epilogue adds the two column halves
@@ -97,7 +95,7 @@ __host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, int resize, int skip_resize, bool tma, Geo* g,
-                     int prefer_mt = 0, int prec = 0, bool epi_tma = false) {
+                     int prefer_mt = 0, int prec = 0) {
   if (c_in <= 0 || c_in % KBLK || c_out <= 0 || c_out % 16 || c_skip % KBLK) return false;
   g->n_tiles = (c_out + 255) / 256;
   if (c_out % g->n_tiles) return false;
@@ -149,22 +147,14 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   }
   // ---- shared-memory plan: one persistent CTA per SM -----------------------------------------
   g->raw_kb_bytes = g->raw_slot_bytes;
-  static const int reserve_kb = getenv("VQVS_SMEM_RESERVE_KB") ? atoi(getenv("VQVS_SMEM_RESERVE_KB")) : 0;  // tuning aid: what a staging area of this size would cost the rings
-  const int budget = 225 * 1024 + 512 - reserve_kb * 1024;  // (of the 227 KB a CTA may opt into)
+  const int budget = 225 * 1024 + 512;  // (of the 227 KB a CTA may opt into)
   int off = SMEM_HEADER;
   g->off_stat = off;
   g->off_ss = off;   off += c_in * 8;
   g->off_bias = off; off += g->n_tile * 4;
   off = align_up(off, 128);
-  const long long w_img = g->per_tile_bytes;
-  // TMA-store epilogue (32 KB of output staging): measured per layer against the direct stores (tools/op_profile.py A/B) it
-  // gains 3-10 % wherever the rings do not feel the loss, and costs 2-9 % on the un-resampled 64-channel layers with resident
-  // weights, whose staging ring drops from three slots to two -- those keep the direct stores.
-  if (epi_tma && resize == VQVS_RESIZE_NONE && g->n_tiles == 1 && g->n_tile <= 64 && w_img <= 90 * 1024) epi_tma = false;
-  g->epi_tma = epi_tma ? 1 : 0;
-  g->off_epi = off;
-  if (epi_tma) off += EPI_WARPS * EPI_STAGE_BYTES;
   g->off_w = off;
+  const long long w_img = g->per_tile_bytes;
   // Resident weights leave room for 2-K-block stages only once the image passes ~90 KB (128 -> 64: 98 KB, 192 -> 64: 147 KB);
   // streaming those through the weight ring with 4-K-block stages and one time tile per item measured 5-18 % faster
   // (profiles/r2_*: the transform warps' per-stage overhead is what the larger stage amortises).  Wider N tiles keep the
@@ -705,16 +695,6 @@ __device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map,
       "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
-// TMA tensor store of one [16 channels x 32 positions] fp32 box from shared memory (bulk-group completion); positions
-// beyond the sequence end are clipped by the hardware.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(x), "r"(y), "r"(src)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -933,8 +913,7 @@ struct Ring {  // running (slot, phase) of an mbarrier ring: no integer division
 template <int MT, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
-                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb,
-                 const __grid_constant__ CUtensorMap tm_out, const VqvsConv d,
+                 const __grid_constant__ CUtensorMap tm_sa, const __grid_constant__ CUtensorMap tm_sb, const VqvsConv d,
                  const Geo g, const VqvsGnFinalize fin) {
   // KIND 3 = PLAIN and additionally no 1x1-skip stages and resident weights (conv1 and identity-skip conv2 of every
   // 64-channel layer: the largest share of a step)
@@ -1011,7 +990,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       if (d.s_b) tma_prefetch_desc(&tm_sb);
     }
   }
-  if (warp == EPI_WARP0 && lane == 0 && LEAN && g.epi_tma) tma_prefetch_desc(&tm_out);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1500,12 +1478,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       };
       const int row = quarter * 32 + lane;
       const int skip_shift = d.skip_resize == VQVS_RESIZE_UP2 ? 1 : 0;
-      // TMA-store epilogue (LEAN kinds): a piece's 8 values go to this warp's staging half [16 channels][32 positions] with
-      // immediate offsets (no address arithmetic, no strided STG), and every second piece one lane stores the 2 KB box;
-      // the two halves alternate, so a half is rewritten only after the store that read it (wait_group.read 1).
-      const bool epi_tma = LEAN && g.epi_tma;  // decided per layer on the host (Geo::epi_tma)
-      float* stage = reinterpret_cast<float*>(smem + g.off_epi + (warp - EPI_WARP0) * EPI_STAGE_BYTES) + lane;
-      int pair_no = 0;  // running count of 16-channel boxes this warp has stored (selects the staging half)
       const bool stack = NCH == 1 && g.stack;  // only 32/64-channel N tiles of the bf16x3 format are stacked (make_geo)
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
@@ -1617,10 +1589,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(ACC_EMPTY(buf));
               }
-              if (epi_tma && !(sub & 1)) {  // this pair's staging half was read by the store issued two pairs ago
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-              }
               if (t_ok && !(dbg_flags & 16)) {
                 const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
                 const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -1632,11 +1600,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   if (SKIPK != 0) o = add2(o, pack2(sk[2 * i], sk[2 * i + 1]));
                   unpack2(o, v[2 * i], v[2 * i + 1]);
                 }
-                if (epi_tma) {
-                  float* sp8 = stage + ((pair_no & 1) * 16 + (sub & 1) * 8) * 32;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) sp8[i * 32] = v[i];
-                } else {
+                {
                   float* p = op;
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -1652,20 +1616,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
                   }
                 }
               }
-              if (epi_tma) {
-                if (sub & 1) {  // 16 channels staged: one lane stores the box (rows beyond the sequence end are clipped)
-                  fence_proxy_async();
-                  __syncwarp();
-                  if (lane == 0) {
-                    tma_store_2d(&tm_out, smem_u32(stage - lane + (pair_no & 1) * 16 * 32), t0 + j * TILE_M + quarter * 32,
-                                 n * d.c_out + nt * g.n_tile + c0 - 8);
-                    tma_store_commit();
-                  }
-                  ++pair_no;
-                }
-              } else {
-                op += (sub == NSUB - 1 && !W16 ? 8 + 32 * (EPI_SPLIT - 1) : 8) * (ptrdiff_t)ts_out;  // next piece (next chunk of this warp after 4)
-              }
+              op += (sub == NSUB - 1 && !W16 ? 8 + 32 * (EPI_SPLIT - 1) : 8) * (ptrdiff_t)ts_out;  // next piece (next chunk of this warp after 4)
               if (SKIPK != 0 && has_next) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sk[i] = skn[i];
@@ -1675,7 +1626,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
         }
       }
       if (stats && stat_n >= 0) flush(stat_n, stat_nt);
-      if (epi_tma && lane == 0) tma_store_wait_read<0>();  // the staging area must outlive the last store's read
     };
     if (fast) {
       const int skipk = d.skip_mode != VQVS_SKIP_IDENTITY ? 0 : d.skip_resize == VQVS_RESIZE_DOWN2 ? 2 : 1;
@@ -1931,8 +1881,8 @@ static cudaError_t launch_kind_impl(VQVS_LAUNCHER_ARGS) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   if (mt == 2 && KIND != 3)
-    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND>, maps[0], maps[1], maps[2], maps[3], maps[4], *d, *g, *fin);
-  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, KIND>, maps[0], maps[1], maps[2], maps[3], maps[4], *d, *g, *fin);
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<(KIND == 3 ? 1 : 2), KIND>, maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, KIND>, maps[0], maps[1], maps[2], maps[3], *d, *g, *fin);
 }
 #if VQVS_KIND_TU == 0
 cudaError_t launch_kind0(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<0>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
@@ -2119,12 +2069,8 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
   const bool tma = tma_eligible(d);
   const int prec = (d->reserved_ >> VQVS_CONV_PREC_SHIFT) & 3;
   if (prec != VQVS_PREC_BF16X3 && prec != VQVS_PREC_F16) return 0;
-  // TMA-store epilogue: 16-B aligned output rows; skipped when any profiling / ablation switch selects the generic kernel
-  static const bool no_epi_tma = getenv("VQVS_NO_EPI_TMA") != nullptr;
-  const bool epi_tma = tma && !no_epi_tma && d->t_out % 4 == 0 && aligned16(d->out) && !(d->reserved_ & 0x1FF);
   auto geo = [&](int prefer_mt) {
-    if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g, prefer_mt, prec,
-                              epi_tma))
+    if (tma && umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, true, g, prefer_mt, prec))
       return true;
     return umma::make_geo(d->c_a + d->c_b, d->c_out, d->ksize, d->dilation, c_skip, d->resize, d->skip_resize, false, g, prefer_mt, prec);
   };
@@ -2296,7 +2242,7 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
     if (d->skip_mode == VQVS_SKIP_IDENTITY)
       VQVS_CHECK_ARG(d->s_a + d->s_b == d->c_out, "conv(umma): identity skip channel mismatch");
   }
-  alignas(64) CUtensorMap maps[5];
+  alignas(64) CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
   if (g.tma) {
     if ((rc = encode_map(&maps[0], d->xa, d->batch * d->c_a, d->t_in, g.main_box_w))) return rc;
@@ -2305,7 +2251,6 @@ extern "C" int vqvs_conv1d_umma(const VqvsConv* d, void* stream) {
       if ((rc = encode_map(&maps[2], d->sa, d->batch * d->s_a, d->t_skip, g.skip_box_w))) return rc;
       if (d->s_b && (rc = encode_map(&maps[3], d->sb, d->batch * d->s_b, d->t_skip, g.skip_box_w))) return rc;
     }
-    if (g.epi_tma && (rc = encode_map(&maps[4], d->out, d->batch * d->c_out, d->t_out, 32))) return rc;  // boxes of 16 channels x 32 positions
   }
   int sm_count = 0, cc_unused = 0;
   if (device_props(&cc_unused, &sm_count) != VQVS_OK) return VQVS_ECUDA;
