@@ -114,10 +114,9 @@ static bool make_geo(int c_in, int c_out, int ksize, int dilation, int c_skip, i
   // Stacking W_hi and W_lo along N replaces hi*hi + lo*hi + hi*lo (3 MMAs) by A_hi*[W_hi;W_lo] + A_lo*[W_hi;W_lo] (2 MMAs, which
   // also adds the lo*lo term).  Kept for 32-channel tiles; 64-channel tiles issue the three products with the A tile of the
   // second one reused from the collector: same tensor time (51 + 32 + 51 against 2 x 67 clocks), 25 % fewer multiply-adds --
-  // the step runs under the board's power cap, and the freed power came back as +2.9 % SM clock / +2.3 % samples/s
-  // (bench.py A/B on one box) -- and a 64-column accumulator the epilogue reads once.  VQVS_STACK64=1 restores stacking.
-  static const bool stack64 = getenv("VQVS_STACK64") != nullptr;
-  g->stack = (parts == 2 && (g->n_tile == 32 || (g->n_tile == 64 && stack64))) ? 1 : 0;
+  // the step runs under the board's power cap, and the freed power came back as +2.9 % SM clock / +2.6 % samples/s
+  // (bench.py A/B on one box) -- and a 64-column accumulator the epilogue reads once.
+  g->stack = (parts == 2 && g->n_tile == 32) ? 1 : 0;
   int cols = 32;
   while (cols < (g->stack ? 2 : 1) * g->n_tile) cols *= 2;
   g->acc_cols = cols;
@@ -1478,7 +1477,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
       };
       const int row = quarter * 32 + lane;
       const int skip_shift = d.skip_resize == VQVS_RESIZE_UP2 ? 1 : 0;
-      const bool stack = NCH == 1 && g.stack;  // only 32/64-channel N tiles of the bf16x3 format are stacked (make_geo)
+      const bool stack = W16 && g.stack;  // only 32-channel N tiles of the bf16x3 format are stacked (make_geo): compile-time false elsewhere
       TILE_ITER_INIT();
       for (int k_local = 0; k_local < n_my_tiles; ++k_local, TILE_ITER_NEXT()) {
         TILE_COORDS(tile)
