@@ -2089,7 +2089,7 @@ static int umma_geo(const VqvsConv* d, Geo* g) {
     // flight), while the fp16 layers with a 1x1 skip conv (K up to 3*512 + 1024, the longest weight streams) keep two.
     static const bool old_rule = getenv("VQVS_MT_RULE_R1") != nullptr;  // (A/B aid: the rounds-based rule alone)
     if (!old_rule && prec == VQVS_PREC_BF16X3 && g->n_tile <= 128) want1 = true;
-    if (!old_rule && prec == VQVS_PREC_F16 && d->skip_mode == VQVS_SKIP_CONV1X1) want1 = false;
+    if (!old_rule && prec == VQVS_PREC_F16 && d->skip_mode == VQVS_SKIP_CONV1X1 && items2 >= sms) want1 = false;  // (small batches keep the finer items)
     if (want1) {
       Geo g2 = *g;
       if (!geo(1)) *g = g2;  // keep the two-tile plan if a one-tile plan does not fit
