@@ -8,14 +8,15 @@
 // * Weight warp: the operand image pre-split into bf16 hi/lo and pre-arranged by vqvs_pack_conv_weights, resident in
 //   shared memory for the whole CTA when it fits (<= 150 KB), else streamed per K block with cp.async.bulk.
 // * Transform warps (8 + 1 for the halo rows): optional GroupNorm(+FiLM) FINALIZE from the producers' statistics at every
-//   sample change, then per element affine -> erf-form GELU (packed fp32x2 approximation, <= 6.4e-7) -> pool / upsample / concat select -> bf16
-//   hi + lo split, stored K-major, un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so
+//   sample change, then per element affine -> erf-form GELU (packed fp32x2 approximation, <= 6.4e-7) -> pool / upsample /
+//   concat select -> bf16 hi + lo split (or fp16), stored K-major, un-swizzled, as [chunk of 8 channels][row = position][16 B].  Rows are 16 B apart, so
 //   the three conv taps are the SAME tile read through descriptors whose start address is shifted by tap*dilation rows --
 //   the halo is staged once.
-// * MMA warp: warp-uniform loop, elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM).  "bf16x3":
-//   hi*hi + lo*hi + hi*lo (~2^-16 relative operand error, measured 1.5e-5 on a whole UNet forward vs 9.7e-4 for single
-//   TF32 -- tools/precision_study.py); for 64-channel N tiles the weight rows are stacked [W_hi ; W_lo] (N = 128) so
-//   that two MMAs per tap give all four products.  Accumulators are double-buffered in TMEM.
+// * MMA warp: warp-uniform loop, elected lane issues tcgen05.mma (kind::f16 -> fp32 in TMEM).  Two operand formats per conv:
+//   "bf16x3" = hi*hi + hi*lo + lo*hi (~2^-16 relative operand error, measured 1.5e-5 on a whole UNet forward vs 9.7e-4 for
+//   single TF32 -- tools/precision_study.py), the second product reusing the A tile from the collector; for 32-channel N
+//   tiles the weight rows are stacked [W_hi ; W_lo] so that two MMAs per tap give all four products; "fp16" = one product
+//   (the deep levels, engine.conv_precision).  Accumulators are double-buffered in TMEM.
 // * Epilogue warps (8): thread = time row.  tcgen05.ld -> + bias (+ lo half) (+ identity skip, prefetched) -> coalesced
 //   stores along time -> GroupNorm (sum, sumsq) of the OUTPUT accumulated in registers across the CTA's tiles, one
 //   accumulator per G-channel granule, reduced across lanes and flushed with fp64 atomics only when the sample changes.
