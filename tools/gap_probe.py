@@ -28,5 +28,26 @@ for spec in sys.argv[1:]:
     clk = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1965
     print("%s: %.2f us per launch back to back; CTA 0 inside the kernel %d clocks (%.2f us at %d MHz), prologue+grid wait %d clocks" %
           (spec, per, pb[5], pb[5] / clk, clk, pb[6]), flush=True)
+    if hasattr(lib, "vqvs_debug_cta"):  # per-CTA timeline of the last launch (profiling build)
+        import numpy as np
+        def timeline():
+            buf = (C.c_uint64 * 640)(); lib.vqvs_debug_cta(buf)
+            a = np.array(list(buf), dtype=np.int64).reshape(160, 4)
+            return a[a[:, 3] > 0]
+        one = (L.Op * 1)(); one[0].kind = conv[0]; one[0].desc = C.addressof(conv[1])
+        runs = []
+        for _ in range(3):
+            L.check(lib.vqvs_run(one, 1, L.stream_ptr())); torch.cuda.synchronize()
+            runs.append(timeline())
+        for a in runs:
+            dur = (a[:, 2] - a[:, 1]) / 1e3
+            end = (a[:, 2] - a[:, 2].min()) / 1e3
+            print("   CTAs %d: busy us min %.1f median %.1f max %.1f; end-time spread %.1f us (median end %.1f before the last); tiles %d..%d" %
+                  (len(a), dur.min(), np.median(dur), dur.max(), end.max(), end.max() - np.median(end), a[:, 3].min(), a[:, 3].max()))
+        # is slowness a property of the SM?  correlation of per-SM busy time between launches
+        d0 = {int(r[0]): (r[2] - r[1]) / r[3] for r in runs[0]}; d1 = {int(r[0]): (r[2] - r[1]) / r[3] for r in runs[1]}
+        k = sorted(set(d0) & set(d1))
+        print("   per-SM time per tile, launch 1 vs 2: correlation %.2f over %d SMs; slowest/fastest SM %.3f" %
+              (np.corrcoef([d0[i] for i in k], [d1[i] for i in k])[0, 1], len(k), max(d0.values()) / min(d0.values())))
     conv[1].reserved_ &= ~512
     del blk, x, plan

@@ -884,6 +884,11 @@ __device__ __forceinline__ bool elect_one() {
 // Optional role profiler (debug flag 512): cycles per phase of block 0, read back with vqvs_debug_prof.
 static __device__ unsigned long long g_prof[32];  // (one copy per translation unit; only the generic kernels' unit writes it)
 #ifdef VQVS_PROF
+static __device__ unsigned long long g_cta[160 * 4];  // per CTA: smid, first-tile-ready clock, end clock (globaltimer ns), tiles
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#endif
+#ifdef VQVS_PROF
 #define PROF_ADD(slot, since) do { if (prof) { const long long now_ = clock64(); acc_[slot] += now_ - (since); (since) = now_; } } while (0)
 #define PROF_DECL(cond) const bool prof = (cond); long long acc_[4] = {0, 0, 0, 0}; long long tprev = prof ? clock64() : 0
 #define PROF_STORE(base) do { if (prof) for (int i_ = 0; i_ < 4; ++i_) g_prof[(base) + i_] = acc_[i_]; } while (0)
@@ -1004,6 +1009,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   if (warp != TMA_W_WARP) asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef VQVS_PROF
   if ((dbg_flags & 512) && blockIdx.x == 0 && threadIdx.x == 0) g_prof[6] = clock64() - prof_t0;  // prologue + wait for the previous grid
+  if ((dbg_flags & 512) && threadIdx.x == 0 && blockIdx.x < 160) {
+    g_cta[blockIdx.x * 4 + 0] = smid();
+    g_cta[blockIdx.x * 4 + 1] = gtime_ns();  // dependent data available
+    g_cta[blockIdx.x * 4 + 3] = n_my_tiles;
+  }
 #endif
 
 // Register budget: 640 threads x 96 registers (the launch bound) for every role.  Per-role budgets via setmaxnreg
@@ -1819,6 +1829,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
   __syncthreads();
 #ifdef VQVS_PROF
   if ((dbg_flags & 512) && blockIdx.x == 0 && threadIdx.x == 0) g_prof[5] = clock64() - prof_t0;  // whole CTA
+  if ((dbg_flags & 512) && threadIdx.x == 0 && blockIdx.x < 160) g_cta[blockIdx.x * 4 + 2] = gtime_ns();
 #endif
   if (warp == MMA_WARP) {
     tc_fence_after();
@@ -1853,6 +1864,12 @@ cudaError_t read_prof(unsigned long long* host32);
 cudaError_t read_prof1(unsigned long long* host32);
 cudaError_t read_prof2(unsigned long long* host32);
 cudaError_t read_prof3(unsigned long long* host32);
+#ifdef VQVS_PROF
+cudaError_t read_cta0(unsigned long long* h);
+cudaError_t read_cta1(unsigned long long* h);
+cudaError_t read_cta2(unsigned long long* h);
+cudaError_t read_cta3(unsigned long long* h);
+#endif
 
 #ifdef VQVS_KIND_TU
 template <int KIND>
@@ -1887,15 +1904,27 @@ static cudaError_t launch_kind_impl(VQVS_LAUNCHER_ARGS) {
 #if VQVS_KIND_TU == 0
 cudaError_t launch_kind0(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<0>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
 cudaError_t read_prof(unsigned long long* host32) { return cudaMemcpyFromSymbol(host32, g_prof, 32 * sizeof(unsigned long long)); }
+#ifdef VQVS_PROF
+cudaError_t read_cta0(unsigned long long* h) { return cudaMemcpyFromSymbol(h, g_cta, 640 * sizeof(unsigned long long)); }
+#endif
 #elif VQVS_KIND_TU == 1
 cudaError_t launch_kind1(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<1>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
 cudaError_t read_prof1(unsigned long long* host32) { return cudaMemcpyFromSymbol(host32, g_prof, 32 * sizeof(unsigned long long)); }
+#ifdef VQVS_PROF
+cudaError_t read_cta1(unsigned long long* h) { return cudaMemcpyFromSymbol(h, g_cta, 640 * sizeof(unsigned long long)); }
+#endif
 #elif VQVS_KIND_TU == 2
 cudaError_t launch_kind2(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<2>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
 cudaError_t read_prof2(unsigned long long* host32) { return cudaMemcpyFromSymbol(host32, g_prof, 32 * sizeof(unsigned long long)); }
+#ifdef VQVS_PROF
+cudaError_t read_cta2(unsigned long long* h) { return cudaMemcpyFromSymbol(h, g_cta, 640 * sizeof(unsigned long long)); }
+#endif
 #else
 cudaError_t launch_kind3(VQVS_LAUNCHER_ARGS) { return launch_kind_impl<3>(mt, grid, smem_bytes, stream, maps, d, g, fin); }
 cudaError_t read_prof3(unsigned long long* host32) { return cudaMemcpyFromSymbol(host32, g_prof, 32 * sizeof(unsigned long long)); }
+#ifdef VQVS_PROF
+cudaError_t read_cta3(unsigned long long* h) { return cudaMemcpyFromSymbol(h, g_cta, 640 * sizeof(unsigned long long)); }
+#endif
 #endif
 }  // namespace umma
 }  // namespace vqvs
@@ -2324,6 +2353,15 @@ extern "C" int vqvs_debug_prof(unsigned long long* host32) {
   }
   return VQVS_OK;
 }
+
+#ifdef VQVS_PROF
+// profiling builds only: per-CTA (smid, start ns, end ns, tiles) of the last profiled launch (flag 512)
+extern "C" int vqvs_debug_cta(unsigned long long* host640) {
+  cudaError_t e = g_last_kind == 3 ? umma::read_cta3(host640) : g_last_kind == 2 ? umma::read_cta2(host640)
+                  : g_last_kind == 1 ? umma::read_cta1(host640) : umma::read_cta0(host640);
+  return e == cudaSuccess ? VQVS_OK : VQVS_ECUDA;
+}
+#endif
 
 extern "C" int vqvs_umma_selftest(const float* a, const float* b, float* dout, int n, int k, int row_shift, int variant,
                                   void* stream) {
