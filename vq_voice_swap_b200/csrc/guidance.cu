@@ -17,9 +17,18 @@
 namespace vqvs {
 
 __device__ __forceinline__ float gelu_grad(float v) {  // d/dv [v * Phi(v)] = Phi(v) + v * phi(v)
-  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
-  const float pdf = 0.3989422804014327f * expf(-0.5f * v * v);
-  return fmaf(v, pdf, cdf);
+  // Phi(-|v|) = 0.5 erfc(|v| / sqrt2) from the same Abramowitz-Stegun 7.1.26 form as gelu_as (|error| <= 1e-7); its
+  // exp(-v^2 / 2) is also the density's, so one ex2 + one rcp serve both terms (erff + expf cost ~3x the instructions).
+  const float av = fabsf(v);
+  const float t = rcp_approx(fmaf(0.2316418882f, av, 1.0f));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float e = ex2_approx((v * v) * -0.72134752044f);  // exp(-v^2 / 2)
+  const float h = (t * p) * e;                             // Phi(-|v|)
+  const float cdf = v >= 0.f ? 1.0f - h : h;
+  return fmaf(v, 0.3989422804014327f * e, cdf);
 }
 
 __device__ __forceinline__ double block_sum(double v, double* red) {  // blockDim.x <= 1024; result valid in thread 0
@@ -87,18 +96,36 @@ __global__ void __launch_bounds__(GB_THREADS) gelu_bwd_kernel(VqvsGeluBwd d) {
   float* q = d.q + (size_t)row * d.t;
   const int t0 = blockIdx.x * GB_CHUNK, t1 = min(d.t, t0 + GB_CHUNK);
   float s1 = 0.f, s2 = 0.f;
-  for (int i = t0 + threadIdx.x; i < t1; i += GB_THREADS) {
-    const float zz = z[i];
-    float g;
-    if (d.up == 1) g = 0.5f * din[i >> 1];
-    else if (d.up == 2) {
-      const float2 pr = *reinterpret_cast<const float2*>(din + 2 * i);
-      g = pr.x + pr.y;
-    } else g = din[i];
-    const float v = g * gelu_grad(fmaf(zz, S, H)) * gf;
-    q[i] = v;
-    s1 += v;
-    s2 = fmaf(v, (zz - mean) * rstd, s2);
+  // 16-byte path: un-resampled gradient, rows 16-byte aligned (these kernels are HBM-bound: 12 B per element)
+  const bool vec = d.up == 0 && (d.t & 3) == 0 && ((reinterpret_cast<uintptr_t>(d.z) | reinterpret_cast<uintptr_t>(d.d_in) |
+                                                   reinterpret_cast<uintptr_t>(d.q)) & 15) == 0;
+  if (vec) {
+    for (int i = t0 + 4 * threadIdx.x; i < t1; i += 4 * GB_THREADS) {
+      const float4 z4 = *reinterpret_cast<const float4*>(z + i), g4 = *reinterpret_cast<const float4*>(din + i);
+      const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = gg[e] * gelu_grad(fmaf(zz[e], S, H)) * gf;
+        s1 += v[e];
+        s2 = fmaf(v[e], (zz[e] - mean) * rstd, s2);
+      }
+      *reinterpret_cast<float4*>(q + i) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int i = t0 + threadIdx.x; i < t1; i += GB_THREADS) {
+      const float zz = z[i];
+      float g;
+      if (d.up == 1) g = 0.5f * din[i >> 1];
+      else if (d.up == 2) {
+        const float2 pr = *reinterpret_cast<const float2*>(din + 2 * i);
+        g = pr.x + pr.y;
+      } else g = din[i];
+      const float v = g * gelu_grad(fmaf(zz, S, H)) * gf;
+      q[i] = v;
+      s1 += v;
+      s2 = fmaf(v, (zz - mean) * rstd, s2);
+    }
   }
   const double r1 = block_sum((double)s1, red), r2 = block_sum((double)s2, red);
   if (threadIdx.x == 0) {
@@ -139,6 +166,26 @@ __global__ void __launch_bounds__(GB_THREADS) affine3_kernel(VqvsAffine3 d) {
   const float* add2 = d.add2 ? d.add2 + (size_t)row * d.t : nullptr;
   float* out = d.out + (size_t)row * d.t;
   const int t0 = blockIdx.x * GB_CHUNK, t1 = min(d.t, t0 + GB_CHUNK);
+  const bool vec = d.add_mode <= 1 && (d.t & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.z) | reinterpret_cast<uintptr_t>(d.out) |
+                     reinterpret_cast<uintptr_t>(d.add) | reinterpret_cast<uintptr_t>(d.add2)) & 15) == 0;
+  if (vec) {  // 16-byte path (12-20 B per element, HBM-bound)
+    for (int i = t0 + 4 * threadIdx.x; i < t1; i += 4 * GB_THREADS) {
+      const float4 q4 = *reinterpret_cast<const float4*>(q + i), z4 = *reinterpret_cast<const float4*>(z + i);
+      float4 o = make_float4(fmaf(A, q4.x, fmaf(B, z4.x, Cc)), fmaf(A, q4.y, fmaf(B, z4.y, Cc)), fmaf(A, q4.z, fmaf(B, z4.z, Cc)),
+                             fmaf(A, q4.w, fmaf(B, z4.w, Cc)));
+      if (d.add_mode == 1) {
+        const float4 a = *reinterpret_cast<const float4*>(add + i);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (add2) {
+        const float4 a = *reinterpret_cast<const float4*>(add2 + i);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = o;
+    }
+    return;
+  }
   for (int i = t0 + threadIdx.x; i < t1; i += GB_THREADS) {
     float v = fmaf(A, q[i], fmaf(B, z[i], Cc));
     if (d.add_mode == 1) v += add[i];
