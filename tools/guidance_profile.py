@@ -34,7 +34,10 @@ for name, plan in (("forward", plans.fwd), ("backward", plans.bwd)):
         for (k, d), ms in zip(plan.descs, acc):
             if k == L.OP_CONV_UMMA:
                 rows.append((ms, "conv^T cin=%d cout=%d t=%d->%d" % (d.c_a + d.c_b, d.c_out, d.t_in, d.t_out)))
-            elif k in (L.OP_GELU_BWD, L.OP_AFFINE3):
-                rows.append((ms, L.OP_NAMES[k]))
-        for ms, what in sorted(rows, reverse=True)[:14]:
+            elif k == L.OP_GELU_BWD:
+                rows.append((ms, "gelu_bwd c=%d t=%d up=%d  (%.0f GB/s)" % (d.c, d.t, d.up, 12.0 * d.batch * d.c * d.t / ms / 1e6)))
+            elif k == L.OP_AFFINE3:
+                rows.append((ms, "affine3 c=%d t=%d add_mode=%d add2=%d  (%.0f GB/s)" % (d.c, d.t, d.add_mode, 1 if d.add2 else 0,
+                             (12.0 + (4 if d.add_mode else 0) + (4 if d.add2 else 0)) * d.batch * d.c * d.t / ms / 1e6)))
+        for ms, what in sorted(rows, reverse=True)[:24]:
             print("      %.3f ms  %s" % (ms, what))
