@@ -266,3 +266,39 @@ def test_audio_io_wav_roundtrip_uses_the_reference_sample_convention(tmp_path):
 
     with pytest.raises(ValueError):
         ChunkReader(str(tmp_path / "a.mp3"), 16000)
+
+
+def test_operand_format_policy(monkeypatch):
+    """engine.conv_precision: the default rule (fp16 single products for C_out >= 4*bc and for 2*bc blocks at <= 1/16 of the input
+    length, bf16x3 elsewhere), the opt-in thresholds and the study knobs, on the unet64 block list."""
+    from vq_voice_swap_b200 import engine
+    from vq_voice_swap_b200 import lib as L
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    for k in ("VQVS_PREC", "VQVS_F16_FROM", "VQVS_F16_SHORT", "VQVS_BF16X3_FIRST", "VQVS_BF16X3_LAST", "VQVS_F16_BLOCKS"):
+        monkeypatch.delenv(k, raising=False)
+    blocks = engine._predictor_blocks(DiffusionModel("unet", 64).predictor)
+    assert len(blocks) == 65
+
+    def policy():
+        rel, out = 1.0, []
+        for b in blocks:
+            rel *= float(b.scale_factor)
+            out.append(engine.conv_precision(b.out_channels, 64, rel))
+        return out
+
+    p = policy()
+    f16 = [i for i, v in enumerate(p) if v == L.PREC_F16]
+    # 128-channel blocks whose output is <= 4000 samples (11-14 down, 46-48 up) + every 256/512-channel block (15-45)
+    assert f16 == list(range(11, 49))
+    assert all(p[i] == L.PREC_BF16X3 for i in list(range(0, 11)) + list(range(49, 65)))
+    assert engine.conv_precision(512, None) == L.PREC_BF16X3  # encoders / single blocks: no reduced formats
+    monkeypatch.setenv("VQVS_F16_SHORT", "0")
+    assert [i for i, v in enumerate(policy()) if v == L.PREC_F16] == list(range(15, 46))
+    monkeypatch.delenv("VQVS_F16_SHORT")
+    monkeypatch.setenv("VQVS_F16_FROM", "2")
+    assert [i for i, v in enumerate(policy()) if v == L.PREC_F16] == list(range(6, 58))
+    monkeypatch.setenv("VQVS_F16_FROM", "1")
+    assert all(v == L.PREC_F16 for v in policy())
+    monkeypatch.setenv("VQVS_PREC", "bf16x3")
+    assert all(v == L.PREC_BF16X3 for v in policy())
