@@ -345,7 +345,7 @@ typedef struct VqvsTimeEmbed {
 } VqvsTimeEmbed;
 int vqvs_time_embed(const VqvsTimeEmbed* d, void* stream);
 
-/* out[i] = GELU(in[i]) (erf form, approximated to <= 4.2e-7 absolute); input of cond_layers when a caller supplies emb directly. */
+/* out[i] = GELU(in[i]) (erf form, approximated to <= 6.4e-7 absolute); input of cond_layers when a caller supplies emb directly. */
 int vqvs_gelu(const float* in, float* out, int64_t n, void* stream);
 
 /* All FiLM Linear layers of a network in one launch: ab[n, :] = W_cat * gelu_emb[n] + b_cat,

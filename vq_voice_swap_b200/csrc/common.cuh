@@ -46,21 +46,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Fast APPROXIMATION of the erf-form GELU used by the CUDA-core prologues.  GELU(x) = x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): measured
-// max |error| 4.2e-7 over [-12, 12] in fp32, tighter than ATen's own fp32 GELU (1.2e-6).
-// Two MUFU ops (rcp, ex2) + 12 FP32 ops per element.
+// Fast APPROXIMATION of the erf-form GELU used by the CUDA-core prologues (the tcgen05 prologue has the packed fp32x2 twin,
+// umma_conv.cu gelu4p).  GELU(x) = max(x, 0) - |x| * Phi(-|x|) with Phi(-a) = 2^P5(a), P5 the weighted-minimax fit of
+// log2 Phi(-a) (tools/fit_gelu_poly.py): |error| <= 4.4e-7 exact, 6.4e-7 as evaluated in fp32 (ATen's own fp32 GELU: 1.2e-6),
+// monotone for all a, so large |x| flush to 0 through ex2(-inf).  One MUFU op + 8 FP32 ops per element.
 __device__ __forceinline__ float gelu_as(float x) {
-  // GELU(x) = max(x, 0) - |x| * h(|x|),  h = 0.5*erfc(|x|/sqrt2) = (0.5*poly(t)) * t * exp(-x^2/2),
-  // t = 1 / (1 + (0.3275911/sqrt2) |x|); the 0.5 and the 1/sqrt2 are folded into the constants.
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.2316418882f, ax, 1.0f));
-  float p = fmaf(0.5307027145f, t, -0.7265760135f);
-  p = fmaf(p, t, 0.7107068705f);
-  p = fmaf(p, t, -0.142248368f);
-  p = fmaf(p, t, 0.127414796f);
-  const float e = ex2_approx((x * x) * -0.72134752044f);
-  const float h = (t * p) * e;
-  return fmaf(-ax, h, fmaxf(x, 0.f));
+  const float n = -fabsf(x);  // Horner in n = -|x|: the odd coefficients of P5 change sign
+  float p = fmaf(4.733092792e-04f, n, 7.084557321e-03f);
+  p = fmaf(p, n, 5.182738230e-02f);
+  p = fmaf(p, n, -4.599924386e-01f);
+  p = fmaf(p, n, 1.150787830e+00f);
+  p = fmaf(p, n, -1.000037670e+00f);
+  return fmaf(n, ex2_approx(p), fmaxf(x, 0.f));
 }
 
 

@@ -17,7 +17,8 @@
 namespace vqvs {
 
 __device__ __forceinline__ float gelu_grad(float v) {  // d/dv [v * Phi(v)] = Phi(v) + v * phi(v)
-  // Phi(-|v|) = 0.5 erfc(|v| / sqrt2) from the same Abramowitz-Stegun 7.1.26 form as gelu_as (|error| <= 1e-7); its
+  // Phi(-|v|) = 0.5 erfc(|v| / sqrt2) in the Abramowitz-Stegun 7.1.26 form (|error| <= 1e-7; Phi itself, not v * Phi, is
+  // needed here, which is what the prologues' 2^P5 fit is NOT tuned for near 0); its
   // exp(-v^2 / 2) is also the density's, so one ex2 + one rcp serve both terms (erff + expf cost ~3x the instructions).
   const float av = fabsf(v);
   const float t = rcp_approx(fmaf(0.2316418882f, av, 1.0f));

@@ -520,7 +520,7 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ uint64_t bcast2(float c) { return pack2(c, c); }
 
-// erf GELU of 4 packed channel pairs.  VQVS_GELU_DEG = 0: the A&S 7.1.26 form of gelu_as (11 packed FP + 4 MUFU per pair).
+// erf GELU of 4 packed channel pairs.  VQVS_GELU_DEG = 0: the Abramowitz-Stegun 7.1.26 form (11 packed FP + 4 MUFU per pair).
 // Default (5): GELU(y) = max(y, 0) - |y| * Phi(-|y|) with Phi(-x) = 2^P(x), P = the weighted-minimax degree-5 fit of
 // log2 Phi(-x) (tools/fit_gelu_poly.py: |GELU error| <= 4.4e-7 exact, 6.4e-7 in this fp32 evaluation; monotone decreasing
 // for all x, so large |y| flush to 0 through ex2(-inf)): 6 packed FP + 2 MUFU + 2 FMNMX per pair.  The transform warps
