@@ -496,6 +496,24 @@ def test_fast_precision_mode_stays_within_north_star(monkeypatch):
     assert 5e-5 < err <= 1e-3  # (the lower bound shows the mode was really applied)
 
 
+def test_fast128_precision_mode_forward(monkeypatch):
+    """VQVS_F16_FROM=2 (bench.py --precision fast128: fp16 single products from 2*bc): a unet64 forward stays well inside the
+    north star's 1e-3 (measured 3.7e-4); like `fast` it is opt-in and never the headline."""
+    monkeypatch.setenv("VQVS_BACKEND", "umma")
+    monkeypatch.setenv("VQVS_F16_FROM", "2")
+    from vq_voice_swap_b200.diffusion_model import DiffusionModel
+
+    m = DiffusionModel("unet", 64)
+    sd = synth.synth_state_dict(synth.shapes_of(m), tag="full64")
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x = synth.normal("full64/x", (1, 1, 64000))
+    ts = torch.tensor([0.62])
+    ref = O.unet_predictor(sd, x, ts)
+    err = rel_l2(m.predictor(x.to(DEV), ts.to(DEV)).cpu(), ref)
+    assert 1.5e-4 < err <= 6e-4
+
+
 def test_batch_64_samples_are_independent(unet64, monkeypatch):
     """Size-independent property at the benchmark batch: sample i of a batch-64 forward equals the same
     sample run alone (every op on the path is per-sample; only atomic summation order may differ)."""
