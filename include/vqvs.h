@@ -403,6 +403,13 @@ int vqvs_run(const VqvsOp* ops, int n_ops, void* stream);
  * in milliseconds (synchronises the stream at the end; measurement aid for bench.py). */
 int vqvs_run_timed(const VqvsOp* ops, int n_ops, void* stream, float* host_ms);
 
+/* Device workspace (bytes) op `kind` (VQVS_OP_*) needs BEYOND the buffers its descriptor names (the library
+ * never allocates, callers size workspaces with this).  Every op works out of its descriptor's buffers and shared
+ * memory -- 0 -- except the attention pool, whose VqvsAttnPool.ws holds vqvs_attnpool_workspace_bytes(batch, c, t, heads)
+ * bytes shared by its forward and backward; the packed conv weight image is a separate, persistent buffer
+ * (vqvs_packed_weight_bytes).  Returns -1 for an unknown kind or a null descriptor. */
+int64_t vqvs_workspace_bytes(int kind, const void* desc);
+
 /* Ops executed by vqvs_run / vqvs_run_timed since the library was loaded, indexed by VQVS_OP_* (32 slots; out32[VQVS_OP_CONV_UMMA] =
  * tcgen05 conv launches, ...; memsets are counted under VQVS_OP_MEMSET).  Evidence hook for the script-level tests and
  * bench.py's gpu_launches: a run that went through a fallback would leave these at zero. */

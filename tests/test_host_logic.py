@@ -302,3 +302,21 @@ def test_operand_format_policy(monkeypatch):
     assert all(v == L.PREC_F16 for v in policy())
     monkeypatch.setenv("VQVS_PREC", "bf16x3")
     assert all(v == L.PREC_BF16X3 for v in policy())
+
+
+def test_workspace_bytes_contract(built):
+    """vqvs_workspace_bytes: 0 for ops that live off their descriptor's buffers, the attention pool's own figure
+    for it, -1 with a message for unknown kinds -- all host-side, no GPU."""
+    from vq_voice_swap_b200 import lib as L
+
+    lib = L.load()
+    conv = L.Conv()
+    assert lib.vqvs_workspace_bytes(L.OP_CONV_UMMA, C.addressof(conv)) == 0
+    ap = L.AttnPool()
+    ap.batch, ap.c, ap.t, ap.heads = 4, 512, 125, 8
+    want = lib.vqvs_attnpool_workspace_bytes(4, 512, 125, 8)
+    assert want > 0 and lib.vqvs_workspace_bytes(L.OP_ATTNPOOL_FWD, C.addressof(ap)) == want
+    assert lib.vqvs_workspace_bytes(L.OP_ATTNPOOL_BWD, C.addressof(ap)) == want
+    assert lib.vqvs_workspace_bytes(99, C.addressof(conv)) == -1
+    assert b"unknown op kind" in lib.vqvs_last_error()
+    assert lib.vqvs_workspace_bytes(L.OP_CONV_UMMA, None) == -1

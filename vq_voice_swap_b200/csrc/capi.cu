@@ -119,6 +119,18 @@ static int run_impl(const VqvsOp* ops, int n_ops, void* stream, cudaEvent_t* ev)
   return VQVS_OK;
 }
 
+extern "C" int64_t vqvs_workspace_bytes(int kind, const void* desc) {
+  if (!desc || kind < VQVS_OP_CONV_SIMT || kind > VQVS_OP_CLS_HEAD_BWD) {
+    vqvs::set_error("vqvs_workspace_bytes: unknown op kind %d or null descriptor", kind);
+    return -1;
+  }
+  if (kind == VQVS_OP_ATTNPOOL_FWD || kind == VQVS_OP_ATTNPOOL_BWD) {
+    const VqvsAttnPool* a = (const VqvsAttnPool*)desc;
+    return vqvs_attnpool_workspace_bytes(a->batch, a->c, a->t, a->heads);
+  }
+  return 0;  // descriptor buffers + shared memory only
+}
+
 extern "C" int vqvs_launch_counts(unsigned long long* out16) {  // 32 slots
   if (!out16) {
     vqvs::set_error("vqvs_launch_counts: null pointer");

@@ -156,6 +156,7 @@ SIGNATURES = {
     "vqvs_conv_in_bwd": (C.c_int, [C.POINTER(ConvInBwd), _p]),
     "vqvs_stride_sample": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "vqvs_attnpool_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vqvs_workspace_bytes": (C.c_int64, [C.c_int, C.c_void_p]),
     "vqvs_attnpool_fwd": (C.c_int, [C.POINTER(AttnPool), _p]),
     "vqvs_attnpool_bwd": (C.c_int, [C.POINTER(AttnPool), _p]),
     "vqvs_cls_head_fwd": (C.c_int, [C.POINTER(ClsHead), _p]),
