@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQVS_ABI_VERSION 6
+#define VQVS_ABI_VERSION 7
 
 #define VQVS_OK 0
 #define VQVS_EINVAL (-1)   /* bad argument / unsupported shape */
