@@ -1030,7 +1030,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constan
     const Src skip_src{d.sa, d.sb, d.s_a, d.s_b, d.t_skip, d.t_out, d.skip_resize};
     Ring ab(g.ab_slots), rw(g.tma ? g.raw_slots : 1);
     int staged_n = -1;
-    PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && xtid == 32);
+#ifndef VQVS_PROF_XWARP
+#define VQVS_PROF_XWARP 0  // which main transform warp the role profiler follows (0..7; warp 12 + n sits on scheduler n % 4)
+#endif
+    PROF_DECL((dbg_flags & 512) && blockIdx.x == 0 && xtid == 32 * (1 + VQVS_PROF_XWARP));
     // per-CTA constants of the two operand sources (main taps / 1x1 skip)
     StageView vm, vs;
     vm.rows = vs.rows = g.rows;
